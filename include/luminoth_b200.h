@@ -1,0 +1,140 @@
+/* luminoth_b200 -- C ABI of the B200-native detection inference engine.
+ *
+ * Drop-in boundary for the Faster R-CNN / SSD predict path of tryolabs/luminoth
+ * (reference = /root/reference/luminoth).  The reference is pure Python on top
+ * of TensorFlow 1.x: its "FFI" for this path is the TF session boundary in
+ *   utils/predicting.py:20-107   graph build + weight restore   -> lumi_create / lumi_set_weight / lumi_finalize
+ *   utils/predicting.py:109-112  session.run(fetches, {image})  -> lumi_predict
+ *   utils/predicting.py:98-107   fetches objects/labels/probs   -> boxes/scores/labels/counts outputs
+ * A maintainer binds these with ctypes.  Plain pointers and
+ * sizes only; no torch / C++ types.  Every function returns 0 on success, a
+ * negative LUMI_E* code otherwise; lumi_last_error() gives the message.
+ *
+ * Threading: one engine = one CUDA stream + workspace, NOT re-entrant (the
+ * Python wrapper holds a lock, like the single tf.Session of the reference).
+ */
+#ifndef LUMINOTH_B200_H
+#define LUMINOTH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LUMI_OK 0
+#define LUMI_EINVAL -1    /* bad argument / unsupported configuration  (ValueError in the wrapper) */
+#define LUMI_ECUDA -2     /* CUDA runtime / driver failure             (RuntimeError) */
+#define LUMI_ESTATE -3    /* call order violated (e.g. predict before finalize) */
+#define LUMI_ENOWEIGHT -4 /* a variable the graph needs was never set  (ValueError) */
+#define LUMI_EOVERFLOW -5 /* an activation left the fp16x2 split range (RuntimeError, never silent) */
+
+typedef struct lumi_engine lumi_engine;
+
+/* Library / device info.  lumi_version: static string.  lumi_device_count: visible CUDA devices (0 without a GPU). */
+const char* lumi_version(void);
+int lumi_device_count(void);
+
+/* Build an engine for the model described by cfg_json = json.dumps(config)
+ * (the merged YAML config, luminoth/utils/config.py:14-22; model.type selects
+ * 'fasterrcnn' | 'ssd' like models/models.py:7-17).  max_batch images per
+ * lumi_predict call, each at most max_h x max_w after preprocessing. */
+int lumi_create(const char* cfg_json, int device, int max_batch, int max_h, int max_w, lumi_engine** out);
+
+/* Feed one TF variable (fp32, HOST pointer) by its checkpoint name, TF layout:
+ * conv [kh,kw,Cin,Cout], linear [in,out], vectors [C].  Replaces
+ * tf.train.Saver.restore (predicting.py:51-63). */
+int lumi_set_weight(lumi_engine* e, const char* tf_var_name, const float* host_data, const int64_t* shape, int ndim);
+
+/* Number of variables the graph needs / names (for the wrapper's random-init path, predicting.py:64-72). */
+int lumi_num_weights(lumi_engine* e);
+int lumi_weight_info(lumi_engine* e, int index, const char** name, int64_t* shape4, int* ndim);
+
+/* Fold BN, split weights into fp16 hi/lo planes, build TMA descriptors, allocate the workspace. */
+int lumi_finalize(lumi_engine* e);
+
+/* Run the forward pass on n images of identical size h x w (already resized
+ * like datasets/object_detection_dataset.py:71-83), RGB, NHWC.
+ *   images      uint8 [n,h,w,3]; host pointer (images_on_device = 0, copied H2D inside)
+ *               or device pointer (images_on_device = 1)
+ *   boxes       float [n, kmax, 4]  (x1,y1,x2,y2) in resized-image pixels
+ *   scores      float [n, kmax]
+ *   labels      int32 [n, kmax]     0-based foreground ids (quirk Q9)
+ *   counts      int32 [n]           valid rows per image
+ * kmax = lumi_max_detections(e).  Outputs are host pointers when
+ * outputs_on_device = 0 (copied D2H + synchronised before returning) or device
+ * pointers (asynchronous on lumi_stream(e)). */
+int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n, int h, int w,
+                 float* boxes, float* scores, int32_t* labels, int32_t* counts, int outputs_on_device);
+
+int lumi_max_detections(lumi_engine* e);
+void* lumi_stream(lumi_engine* e);            /* cudaStream_t the engine launches on */
+int lumi_synchronize(lumi_engine* e);
+/* Kernels launched by the last lumi_predict (our own kernels, for bench.py's gpu_launches). */
+int lumi_last_launch_count(lumi_engine* e);
+
+/* Choose the convolution implementation: 0 = fp32 SIMT implicit GEMM everywhere,
+ * 1 = tcgen05 fp16x2-split tensor-core kernel wherever the layer qualifies (default). */
+int lumi_set_conv_impl(lumi_engine* e, int impl);
+
+/* Debug taps for parity tests (models' debug fetches, predicting.py:104-107):
+ * copy a named intermediate of the LAST lumi_predict to host as fp32.
+ * Names: "conv_feature_map", "rpn_cls_prob", "rpn_bbox_pred", "all_anchors",
+ * "proposals", "proposal_scores", "proposal_counts", "roi_pool", "rcnn_cls_prob",
+ * "rcnn_bbox_offsets", SSD: "cls_prob", "loc_pred", "all_anchors", "fmap_<i>".
+ * Call with out = NULL to query the element count in *numel. */
+int lumi_get_tensor(lumi_engine* e, const char* name, float* out, int64_t capacity, int64_t* numel, int64_t* shape4);
+
+const char* lumi_last_error(lumi_engine* e);  /* e may be NULL: last error of lumi_create */
+void lumi_destroy(lumi_engine* e);
+
+/* ---- stand-alone operators on DEVICE buffers (per-kernel parity tests and
+ * micro-benchmarks; each is one stage of the path, same kernels the engine uses).
+ * All launch on `stream` (cudaStream_t, may be NULL) and synchronise it before returning
+ * (temporaries are released). ---- */
+
+const char* lumi_op_last_error(void);      /* message of the last failed lumi_op_* call on this thread */
+
+/* conv2d NHWC fp32 in/out (converted to/from the fp16x2 split planes internally).
+ * w: TF layout [kh,kw,cin,cout] fp32 on DEVICE.  scale/bias [cout] or NULL.
+ * residual NHWC fp32 [n,ho,wo,cout] or NULL.  act: 0 none, 1 relu, 2 relu6.
+ * padding: 0 VALID, 1 SAME, 2 explicit slim conv2d_same.  impl: 0 SIMT, 1 tcgen05. */
+int lumi_op_conv2d(const float* x, int n, int h, int w, int cin, const float* wgt, int kh, int kw, int cout,
+                   int stride, int rate, int padding, const float* scale, const float* bias,
+                   const float* residual, int act, int impl, float* y, int* ho, int* wo, void* stream);
+
+/* max_pool NHWC fp32. padding 0 VALID / 1 SAME. */
+int lumi_op_max_pool(const float* x, int n, int h, int w, int c, int k, int stride, int padding, float* y, void* stream);
+
+/* ROI crop (2ph x 2pw bilinear) + 2x2 max pool: roi_pool.py:68-95.
+ * rois [r,4] (x1,y1,x2,y2) px of image 0..; roi_batch [r] image index; y [r,ph,pw,c]. */
+int lumi_op_roi_pool(const float* fmap, int n, int fh, int fw, int c, const float* rois, const int32_t* roi_batch,
+                     int r, float im_h, float im_w, int ph, int pw, float* y, void* stream);
+
+/* Sort scores descending (ties: lower index first); idx_out [n] int32. */
+int lumi_op_sort_desc(const float* scores, int n, int32_t* idx_out, void* stream);
+
+/* Greedy NMS == tf.image.non_max_suppression on boxes [n,4] (x1,y1,x2,y2),
+ * ALREADY sorted by score desc.  keep [max_out] int32 indices, *num_keep on device. */
+int lumi_op_nms_sorted(const float* boxes_sorted, int n, float iou_threshold, int max_out,
+                       int32_t* keep, int32_t* num_keep, void* stream);
+
+/* RPN proposal chain (rpn_proposal.py:41-197) for one image: cls_prob [na,2], bbox_pred [na,4],
+ * anchors [na,4] float; outputs proposals [post_nms_top_n,4], scores, count (device). */
+int lumi_op_rpn_proposals(const float* cls_prob, const float* bbox_pred, const float* anchors, int na,
+                          float im_h, float im_w, int pre_nms_top_n, int post_nms_top_n, float nms_threshold,
+                          float min_prob, int filter_outside, int clip_after_nms,
+                          float* proposals, float* scores, int32_t* count, void* stream);
+
+/* Per-class detection chain (rcnn_proposal.py:46-164 when ssd_order = 0; ssd/proposal.py:41-171 when 1)
+ * for one image: boxes_in [r,4] (proposals or anchors), deltas [r,4*nc] (rcnn) or [r,4] (ssd),
+ * cls_prob [r,nc+1]; outputs objects [total_max,4], labels, probs, count (device). */
+int lumi_op_class_detections(const float* boxes_in, const float* deltas, const float* cls_prob, int r, int nc,
+                             float im_h, float im_w, float var0, float var1, float min_prob, float nms_threshold,
+                             int class_max, int total_max, int ssd_order,
+                             float* objects, int32_t* labels, float* probs, int32_t* count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUMINOTH_B200_H */

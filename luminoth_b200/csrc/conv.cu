@@ -1,0 +1,591 @@
+// Convolution kernels of the backbone / RPN / head stack.
+//
+//  * conv_simt_kernel : fp32 implicit GEMM on CUDA cores. Handles every shape
+//    (C_in = 3 stem, stride 2, FC layers); also the on-GPU cross-check of the
+//    tensor-core kernel.
+//  * conv_tc_kernel   : tcgen05 implicit GEMM, stride 1, C_in % 64 == 0.
+//    Activations and weights are fp16 (hi, lo) split planes; each K=16 slice
+//    issues three kind::f16 MMAs  Ahi*Bhi + Ahi*Blo + Alo*Bhi  into one fp32
+//    TMEM accumulator (fp32-class accuracy, SURVEY section 7 "precision").
+//    im2col is fused: the producer issues one 4-D TMA box
+//    {64 ch, tw, th, nb} per filter tap at shifted (possibly negative)
+//    coordinates; out-of-bounds elements are zero-filled by TMA, which IS the
+//    TF SAME zero padding.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer
+//    + TMEM owner, warps 2-5 epilogue (TMEM -> regs -> scale/bias (folded BN)
+//    -> +residual -> relu/relu6 -> hi/lo split -> NHWC store).
+//
+// Replaces slim conv2d+batch_norm+relu (luminoth/models/base/base_network.py:143-151),
+// snt.Conv2D (models/fasterrcnn/rpn.py:69-90, models/ssd/ssd.py:83-96,
+// models/ssd/feature_extractor.py:28-37) and snt.Linear (models/fasterrcnn/rcnn.py:74-98).
+#include "conv.cuh"
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace lumi {
+
+thread_local int g_launch_count = 0;
+
+// =====================================================================================
+// SIMT fp32 implicit GEMM
+// =====================================================================================
+struct SimtArgs {
+  const __half* in_hi; const __half* in_lo;
+  int n, h, w, cin;
+  const float* wgt; const float* scale; const float* bias;
+  int kh, kw, stride, rate, pad_t, pad_l, ho, wo, cout, act;
+  __half* out_hi; __half* out_lo; float* out_f32;
+  const __half* res_hi; const __half* res_lo; int res_h, res_w, res_stride;
+  int* overflow;
+};
+
+constexpr int SM_BM = 128, SM_BN = 64, SM_BK = 16;
+
+__global__ void __launch_bounds__(256) conv_simt_kernel(const SimtArgs a) {
+  __shared__ float As[SM_BK][SM_BM + 4];
+  __shared__ float Bs[SM_BK][SM_BN + 4];
+  const int tid = threadIdx.x;
+  const int M = a.n * a.ho * a.wo;
+  const int K = a.kh * a.kw * a.cin;
+  const int m0 = blockIdx.x * SM_BM, n0 = blockIdx.y * SM_BN;
+
+  // A loader coordinates: one output pixel row, 8 consecutive k
+  const int arow = tid >> 1, akseg = (tid & 1) * 8;
+  const int am = m0 + arow;
+  const bool am_ok = am < M;
+  int a_n = 0, a_oy = 0, a_ox = 0;
+  if (am_ok) { a_n = am / (a.ho * a.wo); int r = am % (a.ho * a.wo); a_oy = r / a.wo; a_ox = r % a.wo; }
+  const bool vec_a = (a.cin % 8) == 0;
+  // B loader coordinates
+  const int bkk = tid >> 4, bnn = (tid & 15) * 4;
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += SM_BK) {
+    // ---- A tile
+    float av[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) av[j] = 0.f;
+    const int kbase = k0 + akseg;
+    if (am_ok && kbase < K) {
+      if (vec_a) {
+        int tap = kbase / a.cin, c = kbase % a.cin;
+        int r = tap / a.kw, s = tap % a.kw;
+        int iy = a_oy * a.stride + r * a.rate - a.pad_t, ix = a_ox * a.stride + s * a.rate - a.pad_l;
+        if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) {
+          size_t off = (((size_t)a_n * a.h + iy) * a.w + ix) * a.cin + c;
+          uint4 vh = *reinterpret_cast<const uint4*>(a.in_hi + off);
+          uint4 vl = *reinterpret_cast<const uint4*>(a.in_lo + off);
+          const __half* ph = reinterpret_cast<const __half*>(&vh);
+          const __half* pl = reinterpret_cast<const __half*>(&vl);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) av[j] = join_f16(ph[j], pl[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int k = kbase + j;
+          if (k < K) {
+            int tap = k / a.cin, c = k % a.cin;
+            int r = tap / a.kw, s = tap % a.kw;
+            int iy = a_oy * a.stride + r * a.rate - a.pad_t, ix = a_ox * a.stride + s * a.rate - a.pad_l;
+            if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) {
+              size_t off = (((size_t)a_n * a.h + iy) * a.w + ix) * a.cin + c;
+              av[j] = join_f16(a.in_hi[off], a.in_lo[off]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) As[akseg + j][arow] = av[j];
+    // ---- B tile
+    {
+      int k = k0 + bkk;
+      float bv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (k < K) {
+        const float* wp = a.wgt + (size_t)k * a.cout + n0 + bnn;
+        if ((a.cout % 4) == 0 && n0 + bnn + 3 < a.cout) {
+          float4 t = *reinterpret_cast<const float4*>(wp);
+          bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n0 + bnn + j < a.cout) bv[j] = wp[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Bs[bkk][bnn + j] = bv[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SM_BK; ++kk) {
+      float ar[8], br[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ar[i] = As[kk][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) br[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+    int n_img = m / (a.ho * a.wo);
+    int r = m % (a.ho * a.wo);
+    int oy = r / a.wo, ox = r % a.wo;
+    size_t obase = (size_t)m * a.cout;
+    size_t rbase = 0;
+    if (a.res_hi)
+      rbase = (((size_t)n_img * a.res_h + (size_t)oy * a.res_stride) * a.res_w + (size_t)ox * a.res_stride) * a.cout;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = n0 + tx * 4 + j;
+      if (c >= a.cout) continue;
+      float sc = a.scale ? a.scale[c] : 1.f;
+      float bi = a.bias ? a.bias[c] : 0.f;
+      float v = fmaf(acc[i][j], sc, bi);
+      if (a.res_hi) v += join_f16(a.res_hi[rbase + c], a.res_lo[rbase + c]);
+      v = apply_act(v, a.act);
+      if (a.out_f32) {
+        a.out_f32[obase + c] = v;
+      } else {
+        if (!(fabsf(v) <= LUMI_F16_MAX) && a.overflow) atomicOr(a.overflow, 1);
+        __half hi, lo;
+        split_f32(v, hi, lo);
+        a.out_hi[obase + c] = hi;
+        a.out_lo[obase + c] = lo;
+      }
+    }
+  }
+}
+
+void launch_conv_simt(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
+  SimtArgs a;
+  a.in_hi = io.in.hi; a.in_lo = io.in.lo;
+  a.n = io.in.n; a.h = io.in.h; a.w = io.in.w; a.cin = io.in.c;
+  LUMI_REQUIRE(io.in.c == L.cin, "conv_simt: channel mismatch");
+  a.wgt = L.w_f32; a.scale = L.scale; a.bias = L.bias;
+  a.kh = L.kh; a.kw = L.kw; a.stride = L.stride; a.rate = L.rate;
+  a.pad_t = io.pad_t; a.pad_l = io.pad_l; a.ho = io.ho; a.wo = io.wo; a.cout = L.cout; a.act = L.act;
+  a.out_hi = io.out.hi; a.out_lo = io.out.lo; a.out_f32 = io.out_f32;
+  a.res_hi = io.res.hi; a.res_lo = io.res.lo; a.res_h = io.res.h; a.res_w = io.res.w; a.res_stride = io.res_stride;
+  a.overflow = io.overflow_flag;
+  long M = (long)a.n * a.ho * a.wo;
+  if (M == 0) return;
+  dim3 grid((unsigned)cdiv64(M, SM_BM), (unsigned)cdiv(L.cout, SM_BN));
+  conv_simt_kernel<<<grid, 256, 0, st>>>(a);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// tcgen05 implicit GEMM (fp16x2 split operands, fp32 TMEM accumulators)
+// =====================================================================================
+struct TcArgs {
+  CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+  const float* scale; const float* bias;
+  __half* out_hi; __half* out_lo; float* out_f32;
+  const __half* res_hi; const __half* res_lo;
+  int res_h, res_w, res_stride;
+  int n, ho, wo, cin, cout;
+  int kh, kw, rate, pad_t, pad_l, act;
+  int nb, th, tw;                  // M tile = nb images x th rows x tw cols (<= 128 pixels)
+  int tiles_w, tiles_h;
+  int* overflow;
+};
+
+constexpr int TC_A_BYTES = 128 * 128;       // 128 pixel rows x 64 fp16 (one 128 B swizzle row each)
+
+template <int BN, int STAGES>
+struct TcCfg {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+  using Cfg = TcCfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;
+  const int tile_x = mt % a.tiles_w;
+  const int tile_y = (mt / a.tiles_w) % a.tiles_h;
+  const int tile_n = mt / (a.tiles_w * a.tiles_h);
+  const int x0 = tile_x * a.tw, y0 = tile_y * a.th, img0 = tile_n * a.nb;
+  const int n0 = blockIdx.y * BN;
+  const int rows_valid = a.nb * a.th * a.tw;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.tm_a_hi); tma_prefetch_desc(&a.tm_a_lo);
+    tma_prefetch_desc(&a.tm_b_hi); tma_prefetch_desc(&a.tm_b_lo);
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int cchunks = a.cin >> 6;
+  const int n_iters = a.kh * a.kw * cchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: one (tap, 64-channel) slice per stage
+      const uint32_t stage_tx = 2u * (uint32_t)rows_valid * 128u + 2u * (uint32_t)Cfg::B_BYTES;
+      int it = 0;
+      for (int tap = 0; tap < a.kh * a.kw; ++tap) {
+        const int r = tap / a.kw, s = tap % a.kw;
+        const int iy = y0 + r * a.rate - a.pad_t, ix = x0 + s * a.rate - a.pad_l;
+        for (int cc = 0; cc < cchunks; ++cc, ++it) {
+          const int st = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&empty_bar[st], ph ^ 1u);
+          uint8_t* sbase = smem + st * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[st], stage_tx);
+          tma_load_4d(sbase, &a.tm_a_hi, &full_bar[st], cc * 64, ix, iy, img0);
+          tma_load_4d(sbase + TC_A_BYTES, &a.tm_a_lo, &full_bar[st], cc * 64, ix, iy, img0);
+          const int kcol = tap * a.cin + cc * 64;
+          tma_load_2d(sbase + 2 * TC_A_BYTES, &a.tm_b_hi, &full_bar[st], kcol, n0);
+          tma_load_2d(sbase + 2 * TC_A_BYTES + Cfg::B_BYTES, &a.tm_b_lo, &full_bar[st], kcol, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer: 4 K-slices x {hi*hi, hi*lo, lo*hi}
+      constexpr uint32_t idesc = make_idesc_f16(128, BN);
+      for (int it = 0; it < n_iters; ++it) {
+        const int st = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
+        const uint64_t d_ahi = make_sw128_kmajor_desc(sa);
+        const uint64_t d_alo = make_sw128_kmajor_desc(sa + TC_A_BYTES);
+        const uint64_t d_bhi = make_sw128_kmajor_desc(sa + 2 * TC_A_BYTES);
+        const uint64_t d_blo = make_sw128_kmajor_desc(sa + 2 * TC_A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ko = (uint64_t)(k * 2);      // 16 fp16 = 32 B = 2 x 16 B units
+          umma_f16(tmem_base, d_ahi + ko, d_bhi + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_f16(tmem_base, d_ahi + ko, d_blo + ko, idesc, 1u);
+          umma_f16(tmem_base, d_alo + ko, d_bhi + ko, idesc, 1u);
+        }
+        umma_commit(&empty_bar[st]);     // frees the smem slot once these MMAs retire
+      }
+      umma_commit(tmem_full_bar);        // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue warps 2..5: TMEM lane quadrant = warp % 4
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    bool valid = row < rows_valid;
+    int n_img = 0, oy = 0, ox = 0;
+    if (valid) {
+      int nl = row / (a.th * a.tw);
+      int rem = row % (a.th * a.tw);
+      n_img = img0 + nl; oy = y0 + rem / a.tw; ox = x0 + rem % a.tw;
+      valid = n_img < a.n && oy < a.ho && ox < a.wo;
+    }
+    const size_t opix = ((size_t)n_img * a.ho + oy) * a.wo + ox;
+    size_t rpix = 0;
+    if (a.res_hi) rpix = ((size_t)n_img * a.res_h + (size_t)oy * a.res_stride) * a.res_w + (size_t)ox * a.res_stride;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      const int c0 = n0 + ch * 32;
+      if (c0 >= a.cout) break;                       // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
+      tmem_ld_wait();
+      if (!valid) continue;
+      float v[32];
+      const bool full = (c0 + 32 <= a.cout);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = c0 + j;
+        const float sc = (full || c < a.cout) ? __ldg(a.scale + c) : 0.f;
+        const float bi = (full || c < a.cout) ? __ldg(a.bias + c) : 0.f;
+        v[j] = fmaf(__uint_as_float(r[j]), sc, bi);
+      }
+      if (a.res_hi) {     // residual tensors always have cout % 32 == 0 channels
+        const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + rpix * a.cout + c0);
+        const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + rpix * a.cout + c0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
+          const __half* ph = reinterpret_cast<const __half*>(&h4);
+          const __half* pl = reinterpret_cast<const __half*>(&l4);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[g * 8 + j] += join_f16(ph[j], pl[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
+      if (a.out_f32) {
+        float* op = a.out_f32 + opix * a.cout + c0;
+        if (full && (a.cout % 4) == 0) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            reinterpret_cast<float4*>(op)[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < a.cout) op[j] = v[j];
+        }
+      } else {            // split outputs always have cout % 32 == 0
+        bool ovf = false;
+        uint4 hv[4], lv[4];
+        __half* ph = reinterpret_cast<__half*>(hv);
+        __half* pl = reinterpret_cast<__half*>(lv);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          ovf |= !(fabsf(v[j]) <= LUMI_F16_MAX);
+          split_f32(v[j], ph[j], pl[j]);
+        }
+        uint4* oh = reinterpret_cast<uint4*>(a.out_hi + opix * a.cout + c0);
+        uint4* ol = reinterpret_cast<uint4*>(a.out_lo + opix * a.cout + c0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { oh[g] = hv[g]; ol[g] = lv[g]; }
+        if (ovf && a.overflow) atomicOr(a.overflow, 1);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host: TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  if (!fn) throw Error(-2, "cuTensorMapEncodeTiled not available from the driver");
+  return fn;
+}
+
+static CUtensorMap make_map_act(const __half* base, int n, int h, int w, int c, int nb, int th, int tw) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(-2, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
+  return m;
+}
+
+static CUtensorMap make_map_wgt(const __half* base, int rows, int kdim, int bn) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kdim * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)bn};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(-2, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+  return m;
+}
+
+// descriptor cache: engine buffers are static, so every (pointer, geometry) repeats each predict call.
+struct MapKey {
+  const void* p; int a, b, c, d, e, f, g;
+  bool operator<(const MapKey& o) const {
+    return std::tie(p, a, b, c, d, e, f, g) < std::tie(o.p, o.a, o.b, o.c, o.d, o.e, o.f, o.g);
+  }
+};
+static std::map<MapKey, CUtensorMap> g_map_cache;
+static std::mutex g_map_mutex;
+
+static CUtensorMap cached_act_map(const __half* base, int n, int h, int w, int c, int nb, int th, int tw) {
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  MapKey k{base, n, h, w, c, nb, th, tw};
+  auto it = g_map_cache.find(k);
+  if (it != g_map_cache.end()) return it->second;
+  if (g_map_cache.size() > 4096) g_map_cache.clear();
+  CUtensorMap m = make_map_act(base, n, h, w, c, nb, th, tw);
+  g_map_cache[k] = m;
+  return m;
+}
+static CUtensorMap cached_wgt_map(const __half* base, int rows, int kdim, int bn) {
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  MapKey k{base, rows, kdim, bn, -1, -1, -1, -1};
+  auto it = g_map_cache.find(k);
+  if (it != g_map_cache.end()) return it->second;
+  CUtensorMap m = make_map_wgt(base, rows, kdim, bn);
+  g_map_cache[k] = m;
+  return m;
+}
+
+// M-tile geometry: (nb, th, tw) with nb*th*tw <= 128 maximising useful rows per tile.
+static void pick_tile(int n, int ho, int wo, int& nb, int& th, int& tw) {
+  double best = -1.0;
+  nb = 1; th = 1; tw = 1;
+  for (int w_ = 1; w_ <= 128 && w_ <= wo; ++w_) {
+    int hmax = 128 / w_;
+    if (hmax > ho) hmax = ho;
+    for (int h_ = 1; h_ <= hmax; ++h_) {
+      int b_ = 1;
+      if (h_ == ho && w_ == wo) { b_ = 128 / (h_ * w_); if (b_ > n) b_ = n; if (b_ < 1) b_ = 1; }
+      long tiles = (long)cdiv(n, b_) * cdiv(ho, h_) * cdiv(wo, w_);
+      double eff = (double)n * ho * wo / ((double)tiles * 128.0);
+      // prefer wide tiles on ties (longer contiguous TMA rows)
+      if (eff > best + 1e-9 || (eff > best - 1e-9 && w_ > tw)) { best = eff; nb = b_; th = h_; tw = w_; }
+    }
+  }
+}
+
+bool conv_tc_supported(const ConvLayer& L, const ConvIO& io) {
+  if (!L.tc_ready) return false;
+  if (L.stride != 1) return false;
+  if (L.cin % 64 != 0) return false;
+  if (io.out_f32 == nullptr && (L.cout % 32) != 0) return false;
+  if (io.res.hi && (L.cout % 32) != 0) return false;
+  return true;
+}
+
+template <int BN, int STAGES>
+static void launch_tc_cfg(const TcArgs& a, dim3 grid, cudaStream_t st) {
+  using Cfg = TcCfg<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LUMI_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  conv_tc_kernel<BN, STAGES><<<grid, 192, Cfg::SMEM_BYTES, st>>>(a);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
+  LUMI_REQUIRE(conv_tc_supported(L, io), "conv_tc: layer not supported by the tensor-core kernel");
+  LUMI_REQUIRE(io.in.c == L.cin, "conv_tc: channel mismatch");
+  if ((long)io.in.n * io.ho * io.wo == 0) return;
+  TcArgs a;
+  std::memset(&a, 0, sizeof(a));
+  int nb, th, tw;
+  pick_tile(io.in.n, io.ho, io.wo, nb, th, tw);
+  const int bn = (L.cout_pad % 256 == 0) ? 256 : (L.cout_pad % 128 == 0 ? 128 : 64);
+  a.tm_a_hi = cached_act_map(io.in.hi, io.in.n, io.in.h, io.in.w, io.in.c, nb, th, tw);
+  a.tm_a_lo = cached_act_map(io.in.lo, io.in.n, io.in.h, io.in.w, io.in.c, nb, th, tw);
+  const int kdim = L.kh * L.kw * L.cin;
+  a.tm_b_hi = cached_wgt_map(L.w_hi, L.cout_pad, kdim, bn);
+  a.tm_b_lo = cached_wgt_map(L.w_lo, L.cout_pad, kdim, bn);
+  a.scale = L.scale_tc; a.bias = L.bias;
+  a.out_hi = io.out.hi; a.out_lo = io.out.lo; a.out_f32 = io.out_f32;
+  a.res_hi = io.res.hi; a.res_lo = io.res.lo; a.res_h = io.res.h; a.res_w = io.res.w; a.res_stride = io.res_stride;
+  a.n = io.in.n; a.ho = io.ho; a.wo = io.wo; a.cin = L.cin; a.cout = L.cout;
+  a.kh = L.kh; a.kw = L.kw; a.rate = L.rate; a.pad_t = io.pad_t; a.pad_l = io.pad_l; a.act = L.act;
+  a.nb = nb; a.th = th; a.tw = tw;
+  a.tiles_w = cdiv(io.wo, tw); a.tiles_h = cdiv(io.ho, th);
+  a.overflow = io.overflow_flag;
+  dim3 grid((unsigned)(a.tiles_w * a.tiles_h * cdiv(io.in.n, nb)), (unsigned)(L.cout_pad / bn));
+  if (bn == 256) launch_tc_cfg<256, 2>(a, grid, st);
+  else if (bn == 128) launch_tc_cfg<128, 3>(a, grid, st);
+  else launch_tc_cfg<64, 4>(a, grid, st);
+}
+
+// ---------------------------------------------------------------- host: weight packing
+void conv_layer_upload(ConvLayer& L, const float* w, const float* scale, const float* bias) {
+  const size_t kdim = (size_t)L.kh * L.kw * L.cin;
+  const size_t nw = kdim * L.cout;
+  LUMI_CUDA_CHECK(cudaMalloc(&L.w_f32, nw * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMemcpy(L.w_f32, w, nw * sizeof(float), cudaMemcpyHostToDevice));
+  std::vector<float> sc(L.cout, 1.f), bi(L.cout, 0.f);
+  if (scale) std::memcpy(sc.data(), scale, L.cout * sizeof(float));
+  if (bias) std::memcpy(bi.data(), bias, L.cout * sizeof(float));
+  LUMI_CUDA_CHECK(cudaMalloc(&L.scale, L.cout * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMalloc(&L.bias, L.cout * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMemcpy(L.scale, sc.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice));
+  LUMI_CUDA_CHECK(cudaMemcpy(L.bias, bi.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice));
+  L.tc_ready = false;
+  if (L.cin % 64 == 0 && L.stride == 1) {
+    // [cout_pad][kdim] fp16 hi/lo of w * 2^e[c]; e[c] puts max|w[:,c]| in [2^13, 2^14)
+    L.cout_pad = cdiv(L.cout, 64) * 64;
+    if (L.cout_pad > 64 && L.cout_pad % 128 != 0) L.cout_pad = cdiv(L.cout, 128) * 128;
+    std::vector<__half> hi((size_t)L.cout_pad * kdim), lo((size_t)L.cout_pad * kdim);
+    std::vector<float> sct(L.cout_pad, 0.f);
+    std::memset(hi.data(), 0, hi.size() * sizeof(__half));
+    std::memset(lo.data(), 0, lo.size() * sizeof(__half));
+    for (int c = 0; c < L.cout; ++c) {
+      float mx = 0.f;
+      for (size_t k = 0; k < kdim; ++k) mx = std::fmax(mx, std::fabs(w[k * L.cout + c]));
+      int e = 0;
+      if (mx > 0.f && std::isfinite(mx)) {
+        int ex;
+        std::frexp(mx, &ex);          // mx = f * 2^ex, f in [0.5,1)
+        e = 14 - ex;                  // mx * 2^e in [2^13, 2^14)
+      }
+      const float up = std::ldexp(1.f, e), down = std::ldexp(1.f, -e);
+      for (size_t k = 0; k < kdim; ++k) {
+        float v = w[k * L.cout + c] * up;
+        __half h = __float2half_rn(v);
+        __half l = __float2half_rn(v - __half2float(h));
+        hi[(size_t)c * kdim + k] = h;
+        lo[(size_t)c * kdim + k] = l;
+      }
+      sct[c] = sc[c] * down;
+    }
+    LUMI_CUDA_CHECK(cudaMalloc(&L.w_hi, hi.size() * sizeof(__half)));
+    LUMI_CUDA_CHECK(cudaMalloc(&L.w_lo, lo.size() * sizeof(__half)));
+    LUMI_CUDA_CHECK(cudaMemcpy(L.w_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    LUMI_CUDA_CHECK(cudaMemcpy(L.w_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    LUMI_CUDA_CHECK(cudaMalloc(&L.scale_tc, L.cout_pad * sizeof(float)));
+    LUMI_CUDA_CHECK(cudaMemcpy(L.scale_tc, sct.data(), L.cout_pad * sizeof(float), cudaMemcpyHostToDevice));
+    L.tc_ready = true;
+  }
+}
+
+void conv_layer_free(ConvLayer& L) {
+  cudaFree(L.w_f32); cudaFree(L.scale); cudaFree(L.bias);
+  cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.scale_tc);
+  L = ConvLayer();
+}
+
+}  // namespace lumi

@@ -1,0 +1,57 @@
+// Convolution layer descriptors shared by the engine and the stand-alone op.
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace lumi {
+
+// One conv layer, device-resident, both weight forms.
+struct ConvLayer {
+  int kh = 1, kw = 1, cin = 0, cout = 0;
+  int stride = 1, rate = 1;
+  int act = ACT_NONE;
+  // SIMT form: TF layout [kh*kw*cin][cout] fp32, epilogue v = acc*scale + bias
+  float* w_f32 = nullptr;
+  float* scale = nullptr;   // [cout]  (BN gamma*rsqrt(var+eps), or 1)
+  float* bias = nullptr;    // [cout]  (BN beta - mean*scale, or conv bias)
+  // tcgen05 form: [cout_pad][kh*kw*cin] fp16 hi/lo planes of w * 2^e[c]; scale_tc = scale * 2^-e[c]
+  __half* w_hi = nullptr;
+  __half* w_lo = nullptr;
+  float* scale_tc = nullptr;
+  int cout_pad = 0;
+  bool tc_ready = false;
+};
+
+struct ConvIO {
+  Act in;
+  Act out;                  // split-plane output (used when out_f32 == nullptr)
+  float* out_f32 = nullptr; // optional fp32 NHWC output [n,ho,wo,cout]
+  Act res;                  // optional residual (res.hi == nullptr -> none)
+  int res_stride = 1;       // residual sampled at (oy*res_stride, ox*res_stride)  (slim `subsample`)
+  int pad_t = 0, pad_l = 0;
+  int ho = 0, wo = 0;
+  int* overflow_flag = nullptr;
+};
+
+// host-side packing (w: TF layout on host)
+void conv_layer_upload(ConvLayer& L, const float* w_host, const float* scale_host, const float* bias_host);
+void conv_layer_free(ConvLayer& L);
+
+bool conv_tc_supported(const ConvLayer& L, const ConvIO& io);
+void launch_conv_simt(const ConvLayer& L, const ConvIO& io, cudaStream_t st);
+void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st);
+
+// TF padding arithmetic
+inline void tf_same(int in, int k, int stride, int rate, int& out, int& pad_before) {
+  int keff = k + (k - 1) * (rate - 1);
+  out = (in + stride - 1) / stride;
+  int total = (out - 1) * stride + keff - in;
+  if (total < 0) total = 0;
+  pad_before = total / 2;
+}
+inline int tf_valid(int in, int k, int stride, int rate) {
+  int keff = k + (k - 1) * (rate - 1);
+  return (in - keff) / stride + 1;
+}
+
+}  // namespace lumi

@@ -1,0 +1,210 @@
+// HBM-bound elementwise / pooling / normalisation kernels (vectorised NHWC).
+#include "ops.cuh"
+
+namespace lumi {
+
+// uint8 RGB image -> (optionally mean-subtracted) fp16x2 planes.
+// base_network.py:153-177 (`inputs - [means]`, only for resnet*/vgg* architectures).
+__global__ void u8_to_act_kernel(const uint8_t* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo,
+                                 size_t numel, int c, float m0, float m1, float m2) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= numel) return;
+  int ch = (int)(i % c);
+  float mean = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
+  float v = __fsub_rn((float)img[i], mean);
+  __half h, l;
+  split_f32(v, h, l);
+  hi[i] = h; lo[i] = l;
+}
+void launch_u8_to_act(const uint8_t* img, Act out, const float* means, cudaStream_t st) {
+  size_t n = out.numel();
+  if (!n) return;
+  float m0 = means ? means[0] : 0.f, m1 = means ? means[1] : 0.f, m2 = means ? means[2] : 0.f;
+  u8_to_act_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(img, out.hi, out.lo, n, out.c, m0, m1, m2);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void f32_to_act_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                                  size_t numel) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= numel) return;
+  __half h, l;
+  split_f32(x[i], h, l);
+  hi[i] = h; lo[i] = l;
+}
+void launch_f32_to_act(const float* x, Act out, cudaStream_t st) {
+  size_t n = out.numel();
+  if (!n) return;
+  f32_to_act_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(x, out.hi, out.lo, n);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void act_to_f32_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ y,
+                                  size_t numel) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= numel) return;
+  y[i] = join_f16(hi[i], lo[i]);
+}
+void launch_act_to_f32(Act in, float* y, cudaStream_t st) {
+  size_t n = in.numel();
+  if (!n) return;
+  act_to_f32_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(in.hi, in.lo, y, n);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+// max pool, 8 channels per thread (C % 8 == 0) -- slim max_pool2d / tf.nn.max_pool.
+// Padded cells are ignored (TF pads with -inf).
+__global__ void max_pool_kernel(const __half* __restrict__ ihi, const __half* __restrict__ ilo,
+                                __half* __restrict__ ohi, __half* __restrict__ olo, int n, int h, int w, int c,
+                                int ho, int wo, int k, int stride, int pad_t, int pad_l) {
+  const int cv = c >> 3;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)n * ho * wo * cv;
+  if (i >= total) return;
+  int c8 = (int)(i % cv);
+  size_t p = i / cv;
+  int ox = (int)(p % wo);
+  int oy = (int)((p / wo) % ho);
+  int ni = (int)(p / ((size_t)wo * ho));
+  float best[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+  for (int r = 0; r < k; ++r) {
+    int iy = oy * stride + r - pad_t;
+    if (iy < 0 || iy >= h) continue;
+    for (int s = 0; s < k; ++s) {
+      int ix = ox * stride + s - pad_l;
+      if (ix < 0 || ix >= w) continue;
+      size_t off = (((size_t)ni * h + iy) * w + ix) * c + (size_t)c8 * 8;
+      uint4 vh = *reinterpret_cast<const uint4*>(ihi + off);
+      uint4 vl = *reinterpret_cast<const uint4*>(ilo + off);
+      const __half* ph = reinterpret_cast<const __half*>(&vh);
+      const __half* pl = reinterpret_cast<const __half*>(&vl);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], join_f16(ph[j], pl[j]));
+    }
+  }
+  uint4 oh, ol;
+  __half* qh = reinterpret_cast<__half*>(&oh);
+  __half* ql = reinterpret_cast<__half*>(&ol);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split_f32(best[j], qh[j], ql[j]);
+  size_t ooff = p * c + (size_t)c8 * 8;
+  *reinterpret_cast<uint4*>(ohi + ooff) = oh;
+  *reinterpret_cast<uint4*>(olo + ooff) = ol;
+}
+void launch_max_pool(Act in, Act out, int k, int stride, int pad_t, int pad_l, cudaStream_t st) {
+  LUMI_REQUIRE(in.c % 8 == 0 && in.c == out.c && in.n == out.n, "max_pool: C must be a multiple of 8");
+  size_t total = (size_t)out.n * out.h * out.w * (out.c / 8);
+  if (!total) return;
+  max_pool_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(in.hi, in.lo, out.hi, out.lo, in.n, in.h, in.w, in.c,
+                                                               out.h, out.w, k, stride, pad_t, pad_l);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+// tf.nn.l2_normalize over channels x gamma (ssd/feature_extractor.py:62-76): one warp per pixel.
+__global__ void l2norm_scale_kernel(const __half* __restrict__ ihi, const __half* __restrict__ ilo,
+                                    __half* __restrict__ ohi, __half* __restrict__ olo,
+                                    const float* __restrict__ gamma, size_t pixels, int c, float eps) {
+  size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= pixels) return;
+  const __half* ph = ihi + warp * c;
+  const __half* pl = ilo + warp * c;
+  float ss = 0.f;
+  for (int j = lane; j < c; j += 32) { float v = join_f16(ph[j], pl[j]); ss = fmaf(v, v, ss); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  float inv = __frcp_rn(__fsqrt_rn(fmaxf(ss, eps)));
+  for (int j = lane; j < c; j += 32) {
+    float v = __fmul_rn(__fmul_rn(join_f16(ph[j], pl[j]), inv), gamma[j]);
+    __half h, l;
+    split_f32(v, h, l);
+    ohi[warp * c + j] = h; olo[warp * c + j] = l;
+  }
+}
+void launch_l2norm_scale(Act in, Act out, const float* gamma, float eps, cudaStream_t st) {
+  size_t pixels = (size_t)in.n * in.h * in.w;
+  if (!pixels) return;
+  l2norm_scale_kernel<<<(unsigned)cdiv64(pixels * 32, 256), 256, 0, st>>>(in.hi, in.lo, out.hi, out.lo, gamma, pixels,
+                                                                         in.c, eps);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+// tf.reduce_mean(features, [1, 2]) (rcnn.py:188)
+__global__ void spatial_mean_kernel(const __half* __restrict__ ihi, const __half* __restrict__ ilo,
+                                    __half* __restrict__ ohi, __half* __restrict__ olo, int rows, int hw, int c) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * c) return;
+  int ch = (int)(i % c);
+  size_t r = i / c;
+  const __half* ph = ihi + r * hw * c + ch;
+  const __half* pl = ilo + r * hw * c + ch;
+  float s = 0.f;
+  for (int p = 0; p < hw; ++p) s += join_f16(ph[(size_t)p * c], pl[(size_t)p * c]);
+  float v = __fdiv_rn(s, (float)hw);
+  __half h, l;
+  split_f32(v, h, l);
+  ohi[i] = h; olo[i] = l;
+}
+void launch_spatial_mean(Act in, Act out, cudaStream_t st) {
+  size_t total = (size_t)in.n * in.c;
+  if (!total) return;
+  spatial_mean_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(in.hi, in.lo, out.hi, out.lo, in.n, in.h * in.w,
+                                                                    in.c);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+// tf.nn.softmax over the first `cols` entries of each row: one warp per row.
+__global__ void softmax_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int rows, int cols,
+                                    int in_stride) {
+  int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (size_t)warp * in_stride;
+  float m = -INFINITY;
+  for (int j = lane; j < cols; j += 32) m = fmaxf(m, xr[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int j = lane; j < cols; j += 32) s += expf(xr[j] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int j = lane; j < cols; j += 32) y[(size_t)warp * cols + j] = __fdiv_rn(expf(xr[j] - m), s);
+}
+void launch_softmax_rows(const float* x, float* y, int rows, int cols, int in_stride, cudaStream_t st) {
+  if (!rows) return;
+  softmax_rows_kernel<<<(unsigned)cdiv64((size_t)rows * 32, 256), 256, 0, st>>>(x, y, rows, cols, in_stride);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+// fasterrcnn.py:261-308 anchors: int32 reference (truncated, quirk Q1) + int32 shifts, cast to float
+// where decode() needs them (bbox_transform_tf.py:6 `tf.cast(bboxes, tf.float32)`).
+__global__ void frcnn_anchors_kernel(const int* __restrict__ ref, int A, int fh, int fw, int stride,
+                                     float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = fh * fw * A;
+  if (i >= total) return;
+  int a = i % A;
+  int cell = i / A;
+  int sx = (cell % fw) * stride, sy = (cell / fw) * stride;
+  float4 v = make_float4((float)(ref[a * 4 + 0] + sx), (float)(ref[a * 4 + 1] + sy), (float)(ref[a * 4 + 2] + sx),
+                         (float)(ref[a * 4 + 3] + sy));
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+void launch_frcnn_anchors(const int* ref, int A, int fh, int fw, int stride, float* out, cudaStream_t st) {
+  int total = fh * fw * A;
+  if (!total) return;
+  frcnn_anchors_kernel<<<cdiv(total, 256), 256, 0, st>>>(ref, A, fh, fw, stride, out);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace lumi

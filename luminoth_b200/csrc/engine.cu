@@ -1,0 +1,1018 @@
+// Engine: builds the Faster R-CNN (slim resnet_v1_{50,101} + RPN + RCNN) or SSD
+// (truncated VGG16 + extras + multibox heads) inference plan from the merged
+// YAML config, owns weights + workspace on one GPU, and runs the forward pass
+// as a fixed sequence of the kernels in conv.cu / elementwise.cu / roi.cu /
+// postproc.cu on one stream.  Exposes the C ABI of include/luminoth_b200.h.
+//
+// Reference structure restated here (not ported):
+//   models/fasterrcnn/fasterrcnn.py:70-156   FasterRCNN._build
+//   models/base/truncated_base_network.py:39-95  endpoint block3 / R101 block4 tail
+//   models/fasterrcnn/rpn.py:136-180, rcnn.py:148-253
+//   models/ssd/ssd.py:37-195, models/ssd/feature_extractor.py:39-132
+#include "../../include/luminoth_b200.h"
+#include "conv.cuh"
+#include "ops.cuh"
+#include "json.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+using namespace lumi;
+
+namespace {
+
+struct HostTensor {
+  std::vector<float> v;
+  std::vector<int64_t> shape;
+};
+
+struct WeightSpec {
+  std::string name;
+  std::vector<int64_t> shape;
+};
+
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, off = 0;
+  void* alloc(size_t bytes, bool dry) {
+    size_t a = (off + 1023) & ~(size_t)1023;
+    off = a + bytes;
+    if (dry) return nullptr;
+    if (off > cap) throw Error(LUMI_ESTATE, "arena overflow (internal)");
+    return base + a;
+  }
+};
+
+struct Tap {
+  const void* ptr = nullptr;   // device
+  int kind = 0;                // 0 f32, 1 Act, 2 int32
+  Act act;
+  int64_t shape[4] = {0, 0, 0, 0};
+};
+
+const int RESNET_UNITS_50[4] = {3, 4, 6, 3};
+const int RESNET_UNITS_101[4] = {3, 4, 23, 3};
+const int BASE_DEPTH[4] = {64, 128, 256, 512};
+const int BLOCK_STRIDE[4] = {2, 2, 2, 1};
+const float RGB_MEANS[3] = {123.68f, 116.78f, 103.94f};
+
+}  // namespace
+
+struct lumi_engine {
+  std::string last_error;
+  JVal cfg;
+  int device = 0, max_batch = 1, max_h = 0, max_w = 0;
+  cudaStream_t stream = nullptr;
+  bool finalized = false;
+  int conv_impl = 1;
+  int launches = 0;
+
+  std::string type, arch;
+  int num_classes = 0;
+  bool with_rcnn = true, use_tail = true, use_mean = true;
+  int output_stride = 16;
+
+  std::vector<WeightSpec> required;
+  std::map<std::string, HostTensor> staged;
+  std::map<std::string, ConvLayer> layers;
+  std::map<std::string, float*> dev_vecs;     // misc device vectors (l2norm gamma)
+
+  // Faster R-CNN
+  int A = 0, anchor_stride = 16;
+  std::vector<int> anchor_ref;                // A x 4 int32 (truncated, quirk Q1)
+  int* d_anchor_ref = nullptr;
+  float* d_anchors = nullptr; int anchors_fh = 0, anchors_fw = 0;
+  RpnParams rpn{};
+  int rpn_channels = 512, rpn_kh = 3, rpn_kw = 3, rpn_act = ACT_RELU6;
+  std::vector<int> fc_sizes; int fc_act = ACT_RELU6;
+  int pooled_w = 7, pooled_h = 7;
+  DetParams det{};
+  int kmax = 0;
+  NmsWorkspace ws_rpn, ws_det;
+  float* d_final_keys = nullptr;
+  // SSD
+  std::vector<int> ssd_app;                   // anchors per point
+  std::vector<float> ssd_anchor_host;
+  float* d_ssd_anchors = nullptr;
+  int ssd_total_anchors = 0;
+  int fixed_h = 300, fixed_w = 300;
+
+  Arena arena;
+  int* d_overflow = nullptr;
+  uint8_t* d_images = nullptr; size_t images_cap = 0;
+  float* d_boxes = nullptr; float* d_scores = nullptr; int* d_labels = nullptr; int* d_counts = nullptr;
+  int* d_prop_counts = nullptr;
+  std::map<std::string, Tap> taps;
+  int planned_n = 0, planned_h = 0, planned_w = 0;
+
+  ~lumi_engine() {
+    for (auto& kv : layers) conv_layer_free(kv.second);
+    for (auto& kv : dev_vecs) cudaFree(kv.second);
+    nms_workspace_free(ws_rpn); nms_workspace_free(ws_det);
+    cudaFree(d_anchor_ref); cudaFree(d_anchors); cudaFree(d_final_keys); cudaFree(d_ssd_anchors);
+    cudaFree(arena.base); cudaFree(d_overflow); cudaFree(d_images);
+    cudaFree(d_boxes); cudaFree(d_scores); cudaFree(d_labels); cudaFree(d_counts); cudaFree(d_prop_counts);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---------------------------------------------------------------- weight specs
+void need(lumi_engine* e, const std::string& name, std::vector<int64_t> shape) {
+  e->required.push_back({name, std::move(shape)});
+}
+void need_bn(lumi_engine* e, const std::string& scope, int c) {
+  for (const char* n : {"gamma", "beta", "moving_mean", "moving_variance"}) need(e, scope + "/BatchNorm/" + n, {c});
+}
+void need_conv_bn(lumi_engine* e, const std::string& scope, int kh, int kw, int cin, int cout) {
+  need(e, scope + "/weights", {kh, kw, cin, cout});
+  need_bn(e, scope, cout);
+}
+
+void spec_resnet(lumi_engine* e) {
+  const std::string root = "truncated_base_network/" + e->arch;
+  const int* units = e->arch == "resnet_v1_50" ? RESNET_UNITS_50 : RESNET_UNITS_101;
+  need_conv_bn(e, root + "/conv1", 7, 7, 3, 64);
+  int cin = 64;
+  const bool tail = e->arch == "resnet_v1_101" && e->use_tail && e->with_rcnn;
+  const int nblocks = tail ? 4 : 3;
+  for (int b = 0; b < nblocks; ++b) {
+    const int bd = BASE_DEPTH[b], depth = bd * 4;
+    for (int u = 0; u < units[b]; ++u) {
+      const std::string s = root + "/block" + std::to_string(b + 1) + "/unit_" + std::to_string(u + 1) + "/bottleneck_v1";
+      if (cin != depth) need_conv_bn(e, s + "/shortcut", 1, 1, cin, depth);
+      need_conv_bn(e, s + "/conv1", 1, 1, cin, bd);
+      need_conv_bn(e, s + "/conv2", 3, 3, bd, bd);
+      need_conv_bn(e, s + "/conv3", 1, 1, bd, depth);
+      cin = depth;
+    }
+  }
+}
+
+const char* VGG_NAMES[5] = {"conv1", "conv2", "conv3", "conv4", "conv5"};
+const int VGG_REPS[5] = {2, 2, 3, 3, 3};
+const int VGG_CH[5] = {64, 128, 256, 512, 512};
+struct Extra { const char* name; int k, cin, cout, stride, rate, valid; };
+const Extra SSD_EXTRAS[10] = {
+    {"conv6", 3, 512, 1024, 1, 6, 0},   {"conv7", 1, 1024, 1024, 1, 1, 0}, {"conv8_1", 1, 1024, 256, 1, 1, 0},
+    {"conv8_2", 3, 256, 512, 2, 1, 0},  {"conv9_1", 1, 512, 128, 1, 1, 0}, {"conv9_2", 3, 128, 256, 2, 1, 0},
+    {"conv10_1", 1, 256, 128, 1, 1, 0}, {"conv10_2", 3, 128, 256, 1, 1, 1}, {"conv11_1", 1, 256, 128, 1, 1, 0},
+    {"conv11_2", 3, 128, 256, 1, 1, 1}};
+const int SSD_FMAP_CH[6] = {512, 1024, 512, 256, 256, 256};
+
+// ---------------------------------------------------------------- config
+int act_from_name(const std::string& n) {
+  if (n == "relu6") return ACT_RELU6;
+  if (n == "relu") return ACT_RELU;
+  throw Error(LUMI_EINVAL, "unsupported activation_function '" + n + "' (relu | relu6)");
+}
+
+void compute_frcnn_anchor_ref(lumi_engine* e) {
+  // utils/anchors.py:4-52 in float64, then truncation toward zero (fasterrcnn.py:299-302, quirk Q1)
+  const double base = e->cfg.number("model.anchors.base_size", 256);
+  std::vector<double> ratios = e->cfg.numbers("model.anchors.ratios");
+  std::vector<double> scales = e->cfg.numbers("model.anchors.scales");
+  LUMI_REQUIRE(!ratios.empty() && !scales.empty(), "model.anchors.ratios/scales must be non-empty lists");
+  e->anchor_ref.clear();
+  for (double r : ratios)
+    for (double s : scales) {
+      const double sq = std::sqrt(r);
+      const double hgt = s * sq * base, wid = s / sq * base;
+      const double a[4] = {0 - (wid - 1) / 2, 0 - (hgt - 1) / 2, 0 + (wid - 1) / 2, 0 + (hgt - 1) / 2};
+      if ((long long)(a[3] - a[1]) == 0 || (long long)(a[2] - a[0]) == 0)
+        throw Error(LUMI_EINVAL, "base_size " + std::to_string((int)base) + " is too small for aspect_ratios and scales.");
+      for (double v : a) e->anchor_ref.push_back((int)std::trunc(v));
+    }
+  e->A = (int)(ratios.size() * scales.size());
+}
+
+void parse_config(lumi_engine* e) {
+  const JVal& c = e->cfg;
+  e->type = c.str("model.type", "");
+  if (e->type != "fasterrcnn" && e->type != "ssd")
+    throw Error(LUMI_EINVAL, "\"" + e->type + "\" is not a valid model_type");
+  e->num_classes = (int)c.number("model.network.num_classes", 0);
+  LUMI_REQUIRE(e->num_classes > 0, "model.network.num_classes must be positive");
+  if (e->type == "fasterrcnn") {
+    e->arch = c.str("model.base_network.architecture", "resnet_v1_101");
+    if (e->arch != "resnet_v1_50" && e->arch != "resnet_v1_101")
+      throw Error(LUMI_EINVAL, "base_network.architecture '" + e->arch +
+                                   "' is not built yet (resnet_v1_50 | resnet_v1_101)");
+    const JVal* ep = c.find("model.base_network.endpoint");
+    if (ep && ep->t == JVal::Str && ep->s != "block3") throw Error(LUMI_EINVAL, "only endpoint block3 is supported");
+    e->with_rcnn = c.boolean("model.network.with_rcnn", false);
+    e->use_tail = c.boolean("model.base_network.use_tail", true);
+    e->output_stride = (int)c.number("model.base_network.output_stride", 16);
+    LUMI_REQUIRE(e->output_stride == 16, "only output_stride 16 is supported");
+    e->anchor_stride = (int)c.number("model.anchors.stride", 16);
+    compute_frcnn_anchor_ref(e);
+    e->rpn_channels = (int)c.number("model.rpn.num_channels", 512);
+    std::vector<double> ks = c.numbers("model.rpn.kernel_shape");
+    if (ks.size() == 2) { e->rpn_kh = (int)ks[0]; e->rpn_kw = (int)ks[1]; }
+    e->rpn_act = act_from_name(c.str("model.rpn.activation_function", "relu6"));
+    RpnParams& r = e->rpn;
+    r.pre_nms_top_n = (int)c.number("model.rpn.proposals.pre_nms_top_n", 12000);
+    r.post_nms_top_n = (int)c.number("model.rpn.proposals.post_nms_top_n", 2000);
+    r.apply_nms = c.boolean("model.rpn.proposals.apply_nms", true);
+    r.nms_threshold = (float)c.number("model.rpn.proposals.nms_threshold", 0.7);
+    r.min_prob = (float)c.number("model.rpn.proposals.min_prob_threshold", 0.0);
+    r.filter_outside = c.boolean("model.rpn.proposals.filter_outside_anchors", false);
+    r.clip_after_nms = c.boolean("model.rpn.proposals.clip_after_nms", false);
+    LUMI_REQUIRE(r.pre_nms_top_n > 0 && r.post_nms_top_n > 0, "pre/post_nms_top_n must be positive");
+    if (!r.apply_nms) r.post_nms_top_n = r.pre_nms_top_n;   // rpn_proposal.py:172-174: all sorted top-n survive
+    e->kmax = r.post_nms_top_n;
+    if (e->with_rcnn) {
+      for (double v : c.numbers("model.rcnn.layer_sizes")) e->fc_sizes.push_back((int)v);
+      e->fc_act = act_from_name(c.str("model.rcnn.activation_function", "relu6"));
+      e->use_mean = c.boolean("model.rcnn.use_mean", true);
+      std::string mode = c.str("model.rcnn.roi.pooling_mode", "crop");
+      std::transform(mode.begin(), mode.end(), mode.begin(), ::tolower);
+      if (mode != "crop") throw Error(LUMI_EINVAL, "Pooling mode " + mode + " is not implemented (roi_pool.py:97-102)");
+      e->pooled_w = (int)c.number("model.rcnn.roi.pooled_width", 7);
+      e->pooled_h = (int)c.number("model.rcnn.roi.pooled_height", 7);
+      LUMI_REQUIRE(c.str("model.rcnn.roi.padding", "VALID") == "VALID", "roi.padding must be VALID");
+      DetParams& d = e->det;
+      d.nc = e->num_classes;
+      std::vector<double> var = c.numbers("model.rcnn.target_normalization_variances");
+      d.var0 = var.size() == 2 ? (float)var[0] : 1.f;
+      d.var1 = var.size() == 2 ? (float)var[1] : 1.f;
+      d.min_prob = (float)c.number("model.rcnn.proposals.min_prob_threshold", 0.0);
+      d.nms_threshold = (float)c.number("model.rcnn.proposals.class_nms_threshold", 0.5);
+      d.class_max = (int)c.number("model.rcnn.proposals.class_max_detections", 100);
+      d.total_max = (int)c.number("model.rcnn.proposals.total_max_detections", 300);
+      d.shared_deltas = 0;
+      e->kmax = d.total_max;
+    }
+  } else {
+    e->arch = c.str("model.base_network.architecture", "truncated_vgg_16");
+    if (e->arch != "truncated_vgg_16") throw Error(LUMI_EINVAL, "Invalid architecture \"" + e->arch + "\"");
+    e->fixed_h = (int)c.number("dataset.image_preprocessing.fixed_height", 300);
+    e->fixed_w = (int)c.number("dataset.image_preprocessing.fixed_width", 300);
+    for (double v : c.numbers("model.anchors.anchors_per_point")) e->ssd_app.push_back((int)v);
+    LUMI_REQUIRE(e->ssd_app.size() == 6, "model.anchors.anchors_per_point must have 6 entries");
+    DetParams& d = e->det;
+    d.nc = e->num_classes;
+    std::vector<double> var = c.numbers("model.variances");
+    d.var0 = var.size() == 2 ? (float)var[0] : 1.f;
+    d.var1 = var.size() == 2 ? (float)var[1] : 1.f;
+    d.min_prob = (float)c.number("model.proposals.min_prob_threshold", 0.0);
+    d.nms_threshold = (float)c.number("model.proposals.class_nms_threshold", 0.45);
+    d.class_max = (int)c.number("model.proposals.class_max_detections", 100);
+    d.total_max = (int)c.number("model.proposals.total_max_detections", 100);
+    d.shared_deltas = 1;
+    e->kmax = d.total_max;
+  }
+}
+
+void build_specs(lumi_engine* e) {
+  if (e->type == "fasterrcnn") {
+    spec_resnet(e);
+    const std::string r = "fasterrcnn/rpn";
+    need(e, r + "/conv/w", {e->rpn_kh, e->rpn_kw, 1024, e->rpn_channels});
+    need(e, r + "/conv/b", {e->rpn_channels});
+    need(e, r + "/cls_conv/w", {1, 1, e->rpn_channels, 2 * e->A});
+    need(e, r + "/cls_conv/b", {2 * e->A});
+    need(e, r + "/bbox_conv/w", {1, 1, e->rpn_channels, 4 * e->A});
+    need(e, r + "/bbox_conv/b", {4 * e->A});
+    if (e->with_rcnn) {
+      int d = (e->arch == "resnet_v1_101" && e->use_tail) ? 2048 : 1024;
+      if (!e->use_mean) d *= e->pooled_w * e->pooled_h;
+      const std::string c = "fasterrcnn/rcnn";
+      for (size_t i = 0; i < e->fc_sizes.size(); ++i) {
+        need(e, c + "/fc_" + std::to_string(i) + "/w", {d, e->fc_sizes[i]});
+        need(e, c + "/fc_" + std::to_string(i) + "/b", {e->fc_sizes[i]});
+        d = e->fc_sizes[i];
+      }
+      need(e, c + "/fc_classifier/w", {d, e->num_classes + 1});
+      need(e, c + "/fc_classifier/b", {e->num_classes + 1});
+      need(e, c + "/fc_bbox/w", {d, 4 * e->num_classes});
+      need(e, c + "/fc_bbox/b", {4 * e->num_classes});
+    }
+  } else {
+    const std::string s = "ssd/ssd_feature_extractor";
+    int cin = 3;
+    for (int b = 0; b < 5; ++b)
+      for (int r = 0; r < VGG_REPS[b]; ++r) {
+        const std::string p = s + "/vgg_16/" + VGG_NAMES[b] + "/" + VGG_NAMES[b] + "_" + std::to_string(r + 1);
+        need(e, p + "/weights", {3, 3, cin, VGG_CH[b]});
+        need(e, p + "/biases", {VGG_CH[b]});
+        cin = VGG_CH[b];
+      }
+    need(e, s + "/conv_4_3_norm/gamma", {1, 1, 1, 512});
+    for (const Extra& x : SSD_EXTRAS) {
+      need(e, s + "/extra_feature_layers/" + x.name + "/w", {x.k, x.k, x.cin, x.cout});
+      need(e, s + "/extra_feature_layers/" + x.name + "/b", {x.cout});
+    }
+    for (int i = 0; i < 6; ++i) {
+      const std::string n = "ssd/MultiBox_" + std::to_string(i);
+      need(e, n + "_offsets_conv/w", {3, 3, SSD_FMAP_CH[i], 4 * e->ssd_app[i]});
+      need(e, n + "_offsets_conv/b", {4 * e->ssd_app[i]});
+      need(e, n + "_classes_conv/w", {3, 3, SSD_FMAP_CH[i], (e->num_classes + 1) * e->ssd_app[i]});
+      need(e, n + "_classes_conv/b", {(e->num_classes + 1) * e->ssd_app[i]});
+    }
+  }
+}
+
+// ---------------------------------------------------------------- finalize helpers
+const HostTensor& W(lumi_engine* e, const std::string& name) {
+  auto it = e->staged.find(name);
+  if (it == e->staged.end()) throw Error(LUMI_ENOWEIGHT, "variable '" + name + "' was never set");
+  return it->second;
+}
+
+// conv + folded inference BN (slim batch_norm, eps 1e-5): y = conv*s + (beta - mean*s), s = gamma/sqrt(var+eps)
+void make_conv_bn(lumi_engine* e, const std::string& scope, int stride, int rate, int act) {
+  const HostTensor& w = W(e, scope + "/weights");
+  ConvLayer L;
+  L.kh = (int)w.shape[0]; L.kw = (int)w.shape[1]; L.cin = (int)w.shape[2]; L.cout = (int)w.shape[3];
+  L.stride = stride; L.rate = rate; L.act = act;
+  const HostTensor& g = W(e, scope + "/BatchNorm/gamma");
+  const HostTensor& b = W(e, scope + "/BatchNorm/beta");
+  const HostTensor& m = W(e, scope + "/BatchNorm/moving_mean");
+  const HostTensor& v = W(e, scope + "/BatchNorm/moving_variance");
+  std::vector<float> sc(L.cout), bi(L.cout);
+  for (int c = 0; c < L.cout; ++c) {
+    const double s = (double)g.v[c] / std::sqrt((double)v.v[c] + 1e-5);
+    sc[c] = (float)s;
+    bi[c] = (float)((double)b.v[c] - (double)m.v[c] * s);
+  }
+  conv_layer_upload(L, w.v.data(), sc.data(), bi.data());
+  e->layers[scope] = L;
+}
+
+// conv + bias (Sonnet / slim-VGG), optionally fusing several same-input convs along C_out
+void make_conv_bias(lumi_engine* e, const std::string& key, const std::vector<std::string>& wnames,
+                    const std::vector<std::string>& bnames, int stride, int rate, int act) {
+  const HostTensor& w0 = W(e, wnames[0]);
+  const bool linear = w0.shape.size() == 2;
+  ConvLayer L;
+  L.kh = linear ? 1 : (int)w0.shape[0]; L.kw = linear ? 1 : (int)w0.shape[1];
+  L.cin = linear ? (int)w0.shape[0] : (int)w0.shape[2];
+  L.stride = stride; L.rate = rate; L.act = act;
+  int cout = 0;
+  for (const auto& n : wnames) cout += (int)W(e, n).shape.back();
+  L.cout = cout;
+  const size_t kdim = (size_t)L.kh * L.kw * L.cin;
+  std::vector<float> w(kdim * cout), b(cout, 0.f);
+  int off = 0;
+  for (size_t i = 0; i < wnames.size(); ++i) {
+    const HostTensor& wi = W(e, wnames[i]);
+    const int co = (int)wi.shape.back();
+    LUMI_REQUIRE(wi.v.size() == kdim * co, "fused conv '" + key + "': weight shapes disagree");
+    for (size_t k = 0; k < kdim; ++k) std::memcpy(&w[k * cout + off], &wi.v[k * co], co * sizeof(float));
+    if (i < bnames.size() && !bnames[i].empty()) {
+      const HostTensor& bi = W(e, bnames[i]);
+      std::memcpy(&b[off], bi.v.data(), co * sizeof(float));
+    }
+    off += co;
+  }
+  conv_layer_upload(L, w.data(), nullptr, b.data());
+  e->layers[key] = L;
+}
+
+void build_layers(lumi_engine* e) {
+  if (e->type == "fasterrcnn") {
+    const std::string root = "truncated_base_network/" + e->arch;
+    const int* units = e->arch == "resnet_v1_50" ? RESNET_UNITS_50 : RESNET_UNITS_101;
+    make_conv_bn(e, root + "/conv1", 2, 1, ACT_RELU);
+    int cin = 64;
+    const bool tail = e->arch == "resnet_v1_101" && e->use_tail && e->with_rcnn;
+    const int nblocks = tail ? 4 : 3;
+    int current = 1, rate = 1;
+    const int target = e->output_stride / 4;
+    for (int b = 0; b < nblocks; ++b) {
+      const int bd = BASE_DEPTH[b], depth = bd * 4;
+      for (int u = 0; u < units[b]; ++u) {
+        const std::string s = root + "/block" + std::to_string(b + 1) + "/unit_" + std::to_string(u + 1) + "/bottleneck_v1";
+        int unit_stride = (u == units[b] - 1) ? BLOCK_STRIDE[b] : 1;
+        int st = unit_stride, rt = 1;
+        if (b == 3) { st = 1; rt = 1; }                       // tail: stack_blocks_dense w/o output_stride, stride 1
+        else if (current == target) { st = 1; rt = rate; rate *= unit_stride; }
+        else { current *= unit_stride; }
+        if (cin != depth) make_conv_bn(e, s + "/shortcut", st, 1, ACT_NONE);
+        make_conv_bn(e, s + "/conv1", 1, 1, ACT_RELU);
+        make_conv_bn(e, s + "/conv2", st, rt, ACT_RELU);
+        make_conv_bn(e, s + "/conv3", 1, 1, ACT_RELU);        // relu applied after the residual add
+        cin = depth;
+      }
+    }
+    const std::string r = "fasterrcnn/rpn";
+    make_conv_bias(e, r + "/conv", {r + "/conv/w"}, {r + "/conv/b"}, 1, 1, e->rpn_act);
+    make_conv_bias(e, r + "/heads", {r + "/cls_conv/w", r + "/bbox_conv/w"}, {r + "/cls_conv/b", r + "/bbox_conv/b"}, 1,
+                   1, ACT_NONE);
+    if (e->with_rcnn) {
+      const std::string c = "fasterrcnn/rcnn";
+      for (size_t i = 0; i < e->fc_sizes.size(); ++i)
+        make_conv_bias(e, c + "/fc_" + std::to_string(i), {c + "/fc_" + std::to_string(i) + "/w"},
+                       {c + "/fc_" + std::to_string(i) + "/b"}, 1, 1, e->fc_act);
+      make_conv_bias(e, c + "/heads", {c + "/fc_classifier/w", c + "/fc_bbox/w"},
+                     {c + "/fc_classifier/b", c + "/fc_bbox/b"}, 1, 1, ACT_NONE);
+    }
+  } else {
+    const std::string s = "ssd/ssd_feature_extractor";
+    for (int b = 0; b < 5; ++b)
+      for (int r = 0; r < VGG_REPS[b]; ++r) {
+        const std::string p = s + "/vgg_16/" + VGG_NAMES[b] + "/" + VGG_NAMES[b] + "_" + std::to_string(r + 1);
+        make_conv_bias(e, p, {p + "/weights"}, {p + "/biases"}, 1, 1, ACT_RELU);
+      }
+    {
+      const HostTensor& g = W(e, s + "/conv_4_3_norm/gamma");
+      float* d = nullptr;
+      LUMI_CUDA_CHECK(cudaMalloc(&d, g.v.size() * sizeof(float)));
+      LUMI_CUDA_CHECK(cudaMemcpy(d, g.v.data(), g.v.size() * sizeof(float), cudaMemcpyHostToDevice));
+      e->dev_vecs["gamma"] = d;
+    }
+    for (const Extra& x : SSD_EXTRAS) {
+      const std::string p = s + "/extra_feature_layers/" + x.name;
+      make_conv_bias(e, p, {p + "/w"}, {p + "/b"}, x.stride, x.rate, ACT_RELU);
+    }
+    for (int i = 0; i < 6; ++i) {
+      const std::string n = "ssd/MultiBox_" + std::to_string(i);
+      make_conv_bias(e, n, {n + "_offsets_conv/w", n + "_classes_conv/w"}, {n + "_offsets_conv/b", n + "_classes_conv/b"},
+                     1, 1, ACT_NONE);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- execution context
+struct Ctx {
+  lumi_engine* e;
+  bool dry;
+  cudaStream_t st;
+  Act act(int n, int h, int w, int c) {
+    Act a; a.n = n; a.h = h; a.w = w; a.c = c;
+    const size_t bytes = a.numel() * sizeof(__half);
+    a.hi = (__half*)e->arena.alloc(bytes, dry);
+    a.lo = (__half*)e->arena.alloc(bytes, dry);
+    return a;
+  }
+  float* f32(size_t count) { return (float*)e->arena.alloc(count * sizeof(float), dry); }
+  void tap_f32(const std::string& name, const float* p, int64_t a, int64_t b, int64_t c, int64_t d) {
+    Tap t; t.ptr = p; t.kind = 0; t.shape[0] = a; t.shape[1] = b; t.shape[2] = c; t.shape[3] = d;
+    e->taps[name] = t;
+  }
+  void tap_act(const std::string& name, Act a) {
+    Tap t; t.kind = 1; t.act = a; t.shape[0] = a.n; t.shape[1] = a.h; t.shape[2] = a.w; t.shape[3] = a.c;
+    e->taps[name] = t;
+  }
+  void tap_i32(const std::string& name, const int* p, int64_t a) {
+    Tap t; t.ptr = p; t.kind = 2; t.shape[0] = a; t.shape[1] = 1; t.shape[2] = 1; t.shape[3] = 1;
+    e->taps[name] = t;
+  }
+};
+
+// padding: 0 VALID, 1 SAME, 2 slim conv2d_same (explicit pad + VALID when stride > 1)
+Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* res, int res_stride, float** out_f32) {
+  auto it = cx.e->layers.find(key);
+  if (it == cx.e->layers.end()) throw Error(LUMI_ESTATE, "layer '" + key + "' missing (internal)");
+  const ConvLayer& L = it->second;
+  ConvIO io;
+  io.in = in;
+  int ho, wo, pt = 0, pl = 0;
+  if (padding == 1 || (padding == 2 && L.stride == 1)) {
+    tf_same(in.h, L.kh, L.stride, L.rate, ho, pt);
+    tf_same(in.w, L.kw, L.stride, L.rate, wo, pl);
+  } else if (padding == 2) {
+    const int keff = L.kh + (L.kh - 1) * (L.rate - 1);
+    pt = pl = (keff - 1) / 2;
+    ho = (in.h + (keff - 1) - keff) / L.stride + 1;
+    wo = (in.w + (keff - 1) - keff) / L.stride + 1;
+  } else {
+    ho = tf_valid(in.h, L.kh, L.stride, L.rate);
+    wo = tf_valid(in.w, L.kw, L.stride, L.rate);
+  }
+  LUMI_REQUIRE(ho > 0 && wo > 0, "conv '" + key + "': input too small");
+  io.pad_t = pt; io.pad_l = pl; io.ho = ho; io.wo = wo;
+  Act out; out.n = in.n; out.h = ho; out.w = wo; out.c = L.cout;
+  if (out_f32) {
+    *out_f32 = cx.f32((size_t)in.n * ho * wo * L.cout);
+    io.out_f32 = *out_f32;
+  } else {
+    out = cx.act(in.n, ho, wo, L.cout);
+    io.out = out;
+  }
+  if (res) { io.res = *res; io.res_stride = res_stride; }
+  io.overflow_flag = cx.e->d_overflow;
+  if (!cx.dry) {
+    if (cx.e->conv_impl == 1 && conv_tc_supported(L, io)) launch_conv_tc(L, io, cx.st);
+    else launch_conv_simt(L, io, cx.st);
+  }
+  return out;
+}
+
+Act run_pool(Ctx& cx, Act in, int k, int stride, bool same) {
+  int ho, wo, pt = 0, pl = 0;
+  if (same) { tf_same(in.h, k, stride, 1, ho, pt); tf_same(in.w, k, stride, 1, wo, pl); }
+  else { ho = tf_valid(in.h, k, stride, 1); wo = tf_valid(in.w, k, stride, 1); }
+  LUMI_REQUIRE(ho > 0 && wo > 0, "max_pool: input too small");
+  Act out = cx.act(in.n, ho, wo, in.c);
+  if (!cx.dry) launch_max_pool(in, out, k, stride, pt, pl, cx.st);
+  return out;
+}
+
+Act bottleneck(Ctx& cx, const std::string& s, Act x, int depth) {
+  const ConvLayer& c2 = cx.e->layers.at(s + "/conv2");
+  const int stride = c2.stride;
+  Act shortcut = x;
+  int res_stride = stride;
+  if (x.c != depth) { shortcut = run_conv(cx, s + "/shortcut", x, 1, nullptr, 1, nullptr); res_stride = 1; }
+  Act r = run_conv(cx, s + "/conv1", x, 1, nullptr, 1, nullptr);
+  r = run_conv(cx, s + "/conv2", r, 2, nullptr, 1, nullptr);
+  return run_conv(cx, s + "/conv3", r, 1, &shortcut, res_stride, nullptr);
+}
+
+// ---------------------------------------------------------------- Faster R-CNN forward
+void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
+  lumi_engine* e = cx.e;
+  const std::string root = "truncated_base_network/" + e->arch;
+  const int* units = e->arch == "resnet_v1_50" ? RESNET_UNITS_50 : RESNET_UNITS_101;
+  Act x = cx.act(n, h, w, 3);
+  if (!cx.dry) launch_u8_to_act(images, x, RGB_MEANS, cx.st);          // base_network.py:153-177
+  x = run_conv(cx, root + "/conv1", x, 2, nullptr, 1, nullptr);          // conv2d_same(64, 7, stride 2) + BN + relu
+  x = run_pool(cx, x, 3, 2, true);                                       // pool1 3x3/2 SAME
+  for (int b = 0; b < 3; ++b)
+    for (int u = 0; u < units[b]; ++u)
+      x = bottleneck(cx, root + "/block" + std::to_string(b + 1) + "/unit_" + std::to_string(u + 1) + "/bottleneck_v1",
+                     x, BASE_DEPTH[b] * 4);
+  const Act fmap = x;                                                    // endpoint block3
+  cx.tap_act("conv_feature_map", fmap);
+  const int fh = fmap.h, fw = fmap.w;
+
+  // anchors (fasterrcnn.py:261-308), regenerated only when the feature-map shape changes
+  const int na = fh * fw * e->A;
+  if (!cx.dry && (e->anchors_fh != fh || e->anchors_fw != fw)) {
+    cudaFree(e->d_anchors);
+    e->d_anchors = nullptr;
+    LUMI_CUDA_CHECK(cudaMalloc(&e->d_anchors, (size_t)na * 4 * sizeof(float)));
+    launch_frcnn_anchors(e->d_anchor_ref, e->A, fh, fw, e->anchor_stride, e->d_anchors, cx.st);
+    e->anchors_fh = fh; e->anchors_fw = fw;
+  }
+  cx.tap_f32("all_anchors", e->d_anchors, na, 4, 1, 1);
+
+  // RPN (rpn.py:136-180): 3x3 conv + act, fused 1x1 heads [cls 2A | bbox 4A], softmax fused into the decode
+  Act rf = run_conv(cx, "fasterrcnn/rpn/conv", fmap, 1, nullptr, 1, nullptr);
+  float* heads = nullptr;
+  run_conv(cx, "fasterrcnn/rpn/heads", rf, 1, nullptr, 1, &heads);
+  const int hc = 6 * e->A;
+  cx.tap_f32("rpn_heads", heads, n, fh * fw, hc, 1);
+
+  RpnParams rp = e->rpn;
+  rp.na = na; rp.im_h = (float)h; rp.im_w = (float)w; rp.logits = 1;
+  rp.cls_stride = hc; rp.cls_off = 0; rp.box_stride = hc; rp.box_off = 2 * e->A;
+  const int post = rp.post_nms_top_n;
+  float* proposals = cx.f32((size_t)n * post * 4);
+  float* pscores = cx.f32((size_t)n * post);
+  if (!cx.dry) {
+    LUMI_REQUIRE(na <= e->ws_rpn.cap, "image too large for the RPN workspace (max_h/max_w at lumi_create)");
+    launch_rpn_proposals(heads, heads, (long)fh * fw * hc, (long)fh * fw * hc, e->A, e->d_anchors, n, rp, e->ws_rpn,
+                         proposals, pscores, e->d_prop_counts, cx.st);
+  }
+  cx.tap_f32("proposals", proposals, n, post, 4, 1);
+  cx.tap_f32("proposal_scores", pscores, n, post, 1, 1);
+  cx.tap_i32("proposal_counts", e->d_prop_counts, n);
+  cx.tap_f32("rpn_sorted_scores", e->ws_rpn.sscores, n, e->ws_rpn.cap, 1, 1);
+  cx.tap_i32("rpn_sorted_counts", e->ws_rpn.nvalid, n);
+
+  if (!e->with_rcnn) {
+    if (!cx.dry) {     // predicting.py:85-92: objects = proposals, probs = scores, labels = 0
+      LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_boxes, proposals, (size_t)n * post * 4 * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, cx.st));
+      LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_scores, pscores, (size_t)n * post * sizeof(float), cudaMemcpyDeviceToDevice,
+                                      cx.st));
+      LUMI_CUDA_CHECK(cudaMemsetAsync(e->d_labels, 0, (size_t)n * post * sizeof(int), cx.st));
+      LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_counts, e->d_prop_counts, n * sizeof(int), cudaMemcpyDeviceToDevice, cx.st));
+    }
+    return;
+  }
+
+  // RCNN (rcnn.py:174-232)
+  Act pooled = cx.act(n * post, e->pooled_w, e->pooled_h, fmap.c);
+  if (!cx.dry)
+    launch_roi_pool(fmap, proposals, e->d_prop_counts, post, (float)h, (float)w, e->pooled_h, e->pooled_w, pooled, cx.st);
+  cx.tap_act("roi_pool", pooled);
+  Act feat = pooled;
+  if (e->arch == "resnet_v1_101" && e->use_tail)                         // truncated_base_network.py:56-95
+    for (int u = 0; u < 3; ++u)
+      feat = bottleneck(cx, root + "/block4/unit_" + std::to_string(u + 1) + "/bottleneck_v1", feat, 2048);
+  if (e->use_mean) {
+    Act m = cx.act(feat.n, 1, 1, feat.c);
+    if (!cx.dry) launch_spatial_mean(feat, m, cx.st);
+    feat = m;
+  } else {
+    feat.c = feat.h * feat.w * feat.c; feat.h = 1; feat.w = 1;           // flatten (NHWC order == tf flatten)
+  }
+  cx.tap_act("rcnn_features", feat);
+  for (size_t i = 0; i < e->fc_sizes.size(); ++i)
+    feat = run_conv(cx, "fasterrcnn/rcnn/fc_" + std::to_string(i), feat, 1, nullptr, 1, nullptr);
+  float* fc = nullptr;
+  run_conv(cx, "fasterrcnn/rcnn/heads", feat, 1, nullptr, 1, &fc);
+  const int C = e->num_classes, fcw = 5 * C + 1;
+  float* cls_prob = cx.f32((size_t)n * post * (C + 1));
+  if (!cx.dry) launch_softmax_rows(fc, cls_prob, n * post, C + 1, fcw, cx.st);
+  cx.tap_f32("rcnn_cls_prob", cls_prob, n, post, C + 1, 1);
+  cx.tap_f32("rcnn_fc", fc, n, post, fcw, 1);
+  DetParams dp = e->det;
+  dp.r = post; dp.im_h = (float)h; dp.im_w = (float)w;
+  dp.prob_stride = C + 1; dp.delta_stride = fcw;
+  if (!cx.dry)
+    launch_class_detections(proposals, (long)post * 4, e->d_prop_counts, fc + (C + 1), cls_prob, n, dp, e->ws_det,
+                            e->d_final_keys, e->d_boxes, e->d_labels, e->d_scores, e->d_counts, cx.st);
+}
+
+// ---------------------------------------------------------------- SSD forward
+__global__ void ssd_repack_kernel(const float* __restrict__ head, int cells, int A, int nc1, int total, int off,
+                                  float* __restrict__ loc, float* __restrict__ cls) {
+  // head [n][cells][4A + nc1*A] -> loc [n][total][4], cls [n][total][nc1] at anchor offset `off`
+  const int img = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_cell = A * (4 + nc1);
+  if (i >= cells * per_cell) return;
+  const int cell = i / per_cell, j = i % per_cell;
+  const float v = head[((size_t)img * cells + cell) * per_cell + j];
+  if (j < 4 * A) {
+    loc[((size_t)img * total + off + (size_t)cell * A) * 4 + j] = v;
+  } else {
+    cls[((size_t)img * total + off + (size_t)cell * A) * nc1 + (j - 4 * A)] = v;
+  }
+}
+
+void ssd_fmap_shapes(int h, int w, int (&fh)[6], int (&fw)[6]) {
+  int a = h, b = w;
+  for (int i = 0; i < 3; ++i) { a = tf_valid(a, 2, 2, 1); b = tf_valid(b, 2, 2, 1); }   // 300 -> 37 (quirk Q8)
+  fh[0] = a; fw[0] = b;
+  a = tf_valid(a, 2, 2, 1); b = tf_valid(b, 2, 2, 1);                                   // 18
+  fh[1] = a; fw[1] = b;
+  int d;
+  tf_same(a, 3, 2, 1, a, d); tf_same(b, 3, 2, 1, b, d); fh[2] = a; fw[2] = b;           // 9
+  tf_same(a, 3, 2, 1, a, d); tf_same(b, 3, 2, 1, b, d); fh[3] = a; fw[3] = b;           // 5
+  a = tf_valid(a, 3, 1, 1); b = tf_valid(b, 3, 1, 1); fh[4] = a; fw[4] = b;             // 3
+  a = tf_valid(a, 3, 1, 1); b = tf_valid(b, 3, 1, 1); fh[5] = a; fw[5] = b;             // 1
+}
+
+void compute_ssd_anchors(lumi_engine* e) {
+  // ssd/utils.py:5-145 + ssd.py:112-129, float64 until the final float32 cast
+  int fh[6], fw[6];
+  ssd_fmap_shapes(e->fixed_h, e->fixed_w, fh, fw);
+  for (int i = 0; i < 6; ++i) LUMI_REQUIRE(fh[i] > 0 && fw[i] > 0, "SSD input too small");
+  const double mn = e->cfg.number("model.anchors.min_scale", 0.1), mx = e->cfg.number("model.anchors.max_scale", 0.88);
+  std::vector<double> ratios = e->cfg.numbers("model.anchors.ratios");
+  double scales[6];
+  const double step = (mx - mn) / 5.0;
+  for (int i = 0; i < 6; ++i) scales[i] = i * step + mn;
+  scales[5] = mx;
+  std::vector<float>& out = e->ssd_anchor_host;
+  out.clear();
+  for (int i = 0; i < 6; ++i) {
+    const int A = e->ssd_app[i];
+    LUMI_REQUIRE((int)ratios.size() >= A - 1, "model.anchors.ratios too short for anchors_per_point");
+    std::vector<double> hs(A), wsz(A);
+    if (i < 5) { hs[0] = wsz[0] = std::sqrt(scales[i] * scales[i + 1]) * fh[i]; }
+    else { hs[0] = scales[i] * fh[i] * 0.99; wsz[0] = scales[i] * fw[i] * 0.99; }
+    for (int a = 1; a < A; ++a) {
+      hs[a] = scales[i] / std::sqrt(ratios[a - 1]) * fh[i];
+      wsz[a] = scales[i] * std::sqrt(ratios[a - 1]) * fw[i];
+    }
+    const double H = e->fixed_h, Wd = e->fixed_w;
+    for (int y = 0; y < fh[i]; ++y)
+      for (int x = 0; x < fw[i]; ++x)
+        for (int a = 0; a < A; ++a) {
+          double b[4] = {0.5 - wsz[a] / 2 + x, 0.5 - hs[a] / 2 + y, 0.5 + wsz[a] / 2 + x, 0.5 + hs[a] / 2 + y};
+          b[0] = b[0] / fw[i] * Wd; b[1] = b[1] / fh[i] * H; b[2] = b[2] / fw[i] * Wd; b[3] = b[3] / fh[i] * H;
+          b[0] = std::fmax(std::fmin(b[0], Wd - 1), 0.0); b[2] = std::fmax(std::fmin(b[2], Wd - 1), 0.0);
+          b[1] = std::fmax(std::fmin(b[1], H - 1), 0.0);  b[3] = std::fmax(std::fmin(b[3], H - 1), 0.0);
+          for (double v : b) out.push_back((float)v);
+        }
+  }
+  e->ssd_total_anchors = (int)(out.size() / 4);
+}
+
+void forward_ssd(Ctx& cx, const uint8_t* images, int n, int h, int w) {
+  lumi_engine* e = cx.e;
+  LUMI_REQUIRE(h == e->fixed_h && w == e->fixed_w, "SSD expects images of the configured fixed size");
+  const std::string s = "ssd/ssd_feature_extractor";
+  Act x = cx.act(n, h, w, 3);
+  if (!cx.dry) launch_u8_to_act(images, x, nullptr, cx.st);             // no mean subtraction (quirk Q7)
+  Act fmaps[6];
+  for (int b = 0; b < 5; ++b) {
+    for (int r = 0; r < VGG_REPS[b]; ++r)
+      x = run_conv(cx, s + "/vgg_16/" + VGG_NAMES[b] + "/" + VGG_NAMES[b] + "_" + std::to_string(r + 1), x, 1, nullptr,
+                   1, nullptr);
+    if (b == 3) {                                                         // conv4_3 -> l2norm x gamma
+      Act nrm = cx.act(x.n, x.h, x.w, x.c);
+      if (!cx.dry) launch_l2norm_scale(x, nrm, e->dev_vecs.at("gamma"), 1e-12f, cx.st);
+      fmaps[0] = nrm;
+    }
+    if (b < 4) x = run_pool(cx, x, 2, 2, false);                          // slim default VALID (quirk Q8)
+  }
+  x = run_pool(cx, x, 3, 1, true);                                        // pool5 3x3/1 SAME
+  const std::string ex = s + "/extra_feature_layers/";
+  int fi = 1;
+  for (int i = 0; i < 10; ++i) {
+    x = run_conv(cx, ex + SSD_EXTRAS[i].name, x, SSD_EXTRAS[i].valid ? 0 : 1, nullptr, 1, nullptr);
+    if (i == 1 || i == 3 || i == 5 || i == 7 || i == 9) fmaps[fi++] = x;
+  }
+  const int C1 = e->num_classes + 1, total = e->ssd_total_anchors;
+  float* loc = cx.f32((size_t)n * total * 4);
+  float* cls = cx.f32((size_t)n * total * C1);
+  int off = 0;
+  for (int i = 0; i < 6; ++i) {
+    cx.tap_act("fmap_" + std::to_string(i), fmaps[i]);
+    float* head = nullptr;
+    Act o = run_conv(cx, "ssd/MultiBox_" + std::to_string(i), fmaps[i], 1, nullptr, 1, &head);
+    const int A = e->ssd_app[i], cells = o.h * o.w, per_cell = A * (4 + C1);
+    if (!cx.dry) {
+      dim3 g(cdiv(cells * per_cell, 256), n);
+      ssd_repack_kernel<<<g, 256, 0, cx.st>>>(head, cells, A, C1, total, off, loc, cls);
+      count_launch();
+      LUMI_CUDA_CHECK(cudaGetLastError());
+    }
+    off += cells * A;
+  }
+  LUMI_REQUIRE(off == total, "SSD anchor count mismatch (internal)");
+  float* prob = cx.f32((size_t)n * total * C1);
+  if (!cx.dry) launch_softmax_rows(cls, prob, n * total, C1, C1, cx.st);
+  cx.tap_f32("loc_pred", loc, n, total, 4, 1);
+  cx.tap_f32("cls_prob", prob, n, total, C1, 1);
+  cx.tap_f32("all_anchors", e->d_ssd_anchors, total, 4, 1, 1);
+  DetParams dp = e->det;
+  dp.r = total; dp.im_h = (float)h; dp.im_w = (float)w; dp.prob_stride = C1; dp.delta_stride = 4;
+  if (!cx.dry)
+    launch_class_detections(e->d_ssd_anchors, 0, nullptr, loc, prob, n, dp, e->ws_det, e->d_final_keys, e->d_boxes,
+                            e->d_labels, e->d_scores, e->d_counts, cx.st);
+}
+
+void forward(Ctx& cx, const uint8_t* images, int n, int h, int w) {
+  cx.e->arena.off = 0;
+  cx.e->taps.clear();
+  if (cx.e->type == "fasterrcnn") forward_frcnn(cx, images, n, h, w);
+  else forward_ssd(cx, images, n, h, w);
+}
+
+int fail(lumi_engine* e, const Error& err) {
+  if (e) e->last_error = err.what(); else g_create_error = err.what();
+  return err.code;
+}
+int fail(lumi_engine* e, int code, const std::string& msg) {
+  if (e) e->last_error = msg; else g_create_error = msg;
+  return code;
+}
+
+#define LUMI_API_BEGIN try {
+#define LUMI_API_END(e)                                                   \
+  }                                                                       \
+  catch (const Error& err) { return fail(e, err); }                       \
+  catch (const std::exception& ex) { return fail(e, LUMI_EINVAL, ex.what()); }
+
+}  // namespace
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" {
+
+const char* lumi_version(void) { return "luminoth_b200 0.1 (sm_100a)"; }
+
+int lumi_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int lumi_create(const char* cfg_json, int device, int max_batch, int max_h, int max_w, lumi_engine** out) {
+  lumi_engine* e = nullptr;
+  LUMI_API_BEGIN
+  LUMI_REQUIRE(cfg_json && out, "lumi_create: null argument");
+  LUMI_REQUIRE(max_batch > 0 && max_h > 0 && max_w > 0, "lumi_create: max_batch/max_h/max_w must be positive");
+  std::unique_ptr<lumi_engine> eng(new lumi_engine());
+  std::string s(cfg_json);
+  eng->cfg = JParser(s).parse();
+  eng->device = device; eng->max_batch = max_batch; eng->max_h = max_h; eng->max_w = max_w;
+  parse_config(eng.get());
+  if (eng->type == "ssd") compute_ssd_anchors(eng.get());
+  build_specs(eng.get());
+  int ndev = lumi_device_count();
+  if (ndev <= 0) throw Error(LUMI_ECUDA, "no CUDA device visible: the luminoth_b200 engine has no CPU fallback");
+  LUMI_REQUIRE(device >= 0 && device < ndev, "lumi_create: invalid device index");
+  LUMI_CUDA_CHECK(cudaSetDevice(device));
+  LUMI_CUDA_CHECK(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+  *out = eng.release();
+  return LUMI_OK;
+  LUMI_API_END(e)
+}
+
+int lumi_set_weight(lumi_engine* e, const char* name, const float* data, const int64_t* shape, int ndim) {
+  if (!e) return LUMI_EINVAL;
+  LUMI_API_BEGIN
+  LUMI_REQUIRE(!e->finalized, "lumi_set_weight after lumi_finalize");
+  LUMI_REQUIRE(name && data && shape && ndim >= 1 && ndim <= 4, "lumi_set_weight: bad argument");
+  const WeightSpec* spec = nullptr;
+  for (const auto& w : e->required) if (w.name == name) { spec = &w; break; }
+  if (!spec) return LUMI_OK;    // variables the inference graph does not use are ignored (Saver(allow_empty) spirit)
+  std::vector<int64_t> shp(shape, shape + ndim);
+  if (shp != spec->shape) {
+    std::string m = "variable '" + std::string(name) + "' has shape [";
+    for (auto d : shp) m += std::to_string(d) + ",";
+    m += "] but the graph expects [";
+    for (auto d : spec->shape) m += std::to_string(d) + ",";
+    throw Error(LUMI_EINVAL, m + "]");
+  }
+  size_t count = 1;
+  for (auto d : shp) count *= (size_t)d;
+  HostTensor t;
+  t.shape = shp;
+  t.v.assign(data, data + count);
+  e->staged[name] = std::move(t);
+  return LUMI_OK;
+  LUMI_API_END(e)
+}
+
+int lumi_num_weights(lumi_engine* e) { return e ? (int)e->required.size() : 0; }
+
+int lumi_weight_info(lumi_engine* e, int index, const char** name, int64_t* shape4, int* ndim) {
+  if (!e || index < 0 || index >= (int)e->required.size()) return LUMI_EINVAL;
+  const WeightSpec& w = e->required[index];
+  if (name) *name = w.name.c_str();
+  if (ndim) *ndim = (int)w.shape.size();
+  if (shape4) for (size_t i = 0; i < 4; ++i) shape4[i] = i < w.shape.size() ? w.shape[i] : 1;
+  return LUMI_OK;
+}
+
+int lumi_finalize(lumi_engine* e) {
+  if (!e) return LUMI_EINVAL;
+  LUMI_API_BEGIN
+  LUMI_REQUIRE(!e->finalized, "lumi_finalize called twice");
+  LUMI_CUDA_CHECK(cudaSetDevice(e->device));
+  for (const auto& w : e->required)
+    if (!e->staged.count(w.name)) throw Error(LUMI_ENOWEIGHT, "variable '" + w.name + "' was never set");
+  build_layers(e);
+  e->staged.clear();
+  LUMI_CUDA_CHECK(cudaMalloc(&e->d_overflow, sizeof(int)));
+  LUMI_CUDA_CHECK(cudaMemset(e->d_overflow, 0, sizeof(int)));
+  const int nb = e->max_batch;
+  LUMI_CUDA_CHECK(cudaMalloc(&e->d_boxes, (size_t)nb * e->kmax * 4 * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMalloc(&e->d_scores, (size_t)nb * e->kmax * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMalloc(&e->d_labels, (size_t)nb * e->kmax * sizeof(int)));
+  LUMI_CUDA_CHECK(cudaMalloc(&e->d_counts, nb * sizeof(int)));
+  LUMI_CUDA_CHECK(cudaMalloc(&e->d_prop_counts, nb * sizeof(int)));
+  if (e->type == "fasterrcnn") {
+    LUMI_CUDA_CHECK(cudaMalloc(&e->d_anchor_ref, e->anchor_ref.size() * sizeof(int)));
+    LUMI_CUDA_CHECK(cudaMemcpy(e->d_anchor_ref, e->anchor_ref.data(), e->anchor_ref.size() * sizeof(int),
+                               cudaMemcpyHostToDevice));
+    const int fh = cdiv(e->max_h, 16), fw = cdiv(e->max_w, 16);
+    nms_workspace_alloc(e->ws_rpn, nb, fh * fw * e->A, e->rpn.post_nms_top_n);
+    if (e->with_rcnn) {
+      nms_workspace_alloc(e->ws_det, nb * e->num_classes, e->rpn.post_nms_top_n, e->det.class_max);
+      const size_t fcap = (size_t)e->num_classes * e->det.class_max;
+      LUMI_CUDA_CHECK(cudaMalloc(&e->d_final_keys, ((size_t)nb * fcap * 2 + nb) * sizeof(float)));
+    }
+  } else {
+    LUMI_CUDA_CHECK(cudaMalloc(&e->d_ssd_anchors, e->ssd_anchor_host.size() * sizeof(float)));
+    LUMI_CUDA_CHECK(cudaMemcpy(e->d_ssd_anchors, e->ssd_anchor_host.data(), e->ssd_anchor_host.size() * sizeof(float),
+                               cudaMemcpyHostToDevice));
+    nms_workspace_alloc(e->ws_det, nb * e->num_classes, e->ssd_total_anchors, e->det.class_max);
+    const size_t fcap = (size_t)e->num_classes * e->det.class_max;
+    LUMI_CUDA_CHECK(cudaMalloc(&e->d_final_keys, ((size_t)nb * fcap * 2 + nb) * sizeof(float)));
+  }
+  e->finalized = true;
+  return LUMI_OK;
+  LUMI_API_END(e)
+}
+
+int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n, int h, int w, float* boxes,
+                 float* scores, int32_t* labels, int32_t* counts, int outputs_on_device) {
+  if (!e) return LUMI_EINVAL;
+  LUMI_API_BEGIN
+  if (!e->finalized) throw Error(LUMI_ESTATE, "lumi_predict before lumi_finalize");
+  LUMI_REQUIRE(images && boxes && scores && labels && counts, "lumi_predict: null buffer");
+  LUMI_REQUIRE(n > 0 && n <= e->max_batch, "lumi_predict: batch size exceeds max_batch");
+  LUMI_REQUIRE(h > 0 && w > 0 && h <= e->max_h && w <= e->max_w, "lumi_predict: image larger than max_h x max_w");
+  LUMI_CUDA_CHECK(cudaSetDevice(e->device));
+  Ctx cx{e, false, e->stream};
+  if (n != e->planned_n || h != e->planned_h || w != e->planned_w) {   // size the arena for this shape
+    Ctx dry{e, true, e->stream};
+    forward(dry, nullptr, n, h, w);
+    const size_t need_bytes = e->arena.off + 4096;
+    if (need_bytes > e->arena.cap) {
+      LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      cudaFree(e->arena.base);
+      e->arena.base = nullptr; e->arena.cap = 0;
+      LUMI_CUDA_CHECK(cudaMalloc(&e->arena.base, need_bytes));
+      e->arena.cap = need_bytes;
+    }
+    e->planned_n = n; e->planned_h = h; e->planned_w = w;
+  }
+  const uint8_t* dimg = static_cast<const uint8_t*>(images);
+  const size_t img_bytes = (size_t)n * h * w * 3;
+  if (!images_on_device) {
+    if (img_bytes > e->images_cap) {
+      LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      cudaFree(e->d_images);
+      e->d_images = nullptr; e->images_cap = 0;
+      LUMI_CUDA_CHECK(cudaMalloc(&e->d_images, img_bytes));
+      e->images_cap = img_bytes;
+    }
+    LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_images, images, img_bytes, cudaMemcpyHostToDevice, e->stream));
+    dimg = e->d_images;
+  }
+  g_launch_count = 0;
+  forward(cx, dimg, n, h, w);
+  e->launches = g_launch_count;
+  const size_t k = (size_t)e->kmax;
+  const cudaMemcpyKind kind = outputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  LUMI_CUDA_CHECK(cudaMemcpyAsync(boxes, e->d_boxes, n * k * 4 * sizeof(float), kind, e->stream));
+  LUMI_CUDA_CHECK(cudaMemcpyAsync(scores, e->d_scores, n * k * sizeof(float), kind, e->stream));
+  LUMI_CUDA_CHECK(cudaMemcpyAsync(labels, e->d_labels, n * k * sizeof(int), kind, e->stream));
+  LUMI_CUDA_CHECK(cudaMemcpyAsync(counts, e->d_counts, n * sizeof(int), kind, e->stream));
+  if (!outputs_on_device) {
+    int ovf = 0;
+    LUMI_CUDA_CHECK(cudaMemcpyAsync(&ovf, e->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (ovf) {
+      LUMI_CUDA_CHECK(cudaMemset(e->d_overflow, 0, sizeof(int)));
+      throw Error(LUMI_EOVERFLOW, "an activation exceeded the fp16x2 split range (|x| > 65504); results are invalid");
+    }
+  }
+  return LUMI_OK;
+  LUMI_API_END(e)
+}
+
+int lumi_max_detections(lumi_engine* e) { return e ? e->kmax : 0; }
+void* lumi_stream(lumi_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int lumi_synchronize(lumi_engine* e) {
+  if (!e) return LUMI_EINVAL;
+  LUMI_API_BEGIN
+  LUMI_CUDA_CHECK(cudaSetDevice(e->device));
+  LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  int ovf = 0;
+  if (e->d_overflow) {
+    LUMI_CUDA_CHECK(cudaMemcpy(&ovf, e->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    if (ovf) {
+      LUMI_CUDA_CHECK(cudaMemset(e->d_overflow, 0, sizeof(int)));
+      throw Error(LUMI_EOVERFLOW, "an activation exceeded the fp16x2 split range (|x| > 65504); results are invalid");
+    }
+  }
+  return LUMI_OK;
+  LUMI_API_END(e)
+}
+
+int lumi_last_launch_count(lumi_engine* e) { return e ? e->launches : 0; }
+
+int lumi_set_conv_impl(lumi_engine* e, int impl) {
+  if (!e || (impl != 0 && impl != 1)) return LUMI_EINVAL;
+  e->conv_impl = impl;
+  return LUMI_OK;
+}
+
+int lumi_get_tensor(lumi_engine* e, const char* name, float* out, int64_t capacity, int64_t* numel, int64_t* shape4) {
+  if (!e) return LUMI_EINVAL;
+  LUMI_API_BEGIN
+  LUMI_REQUIRE(name, "lumi_get_tensor: null name");
+  auto it = e->taps.find(name);
+  if (it == e->taps.end()) throw Error(LUMI_EINVAL, "unknown tensor '" + std::string(name) + "'");
+  const Tap& t = it->second;
+  const int64_t count = t.shape[0] * t.shape[1] * t.shape[2] * t.shape[3];
+  if (numel) *numel = count;
+  if (shape4) for (int i = 0; i < 4; ++i) shape4[i] = t.shape[i];
+  if (!out) return LUMI_OK;
+  LUMI_REQUIRE(capacity >= count, "lumi_get_tensor: output buffer too small");
+  LUMI_CUDA_CHECK(cudaSetDevice(e->device));
+  LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  if (t.kind == 0) {
+    LUMI_CUDA_CHECK(cudaMemcpy(out, t.ptr, count * sizeof(float), cudaMemcpyDeviceToHost));
+  } else if (t.kind == 2) {
+    std::vector<int> tmp(count);
+    LUMI_CUDA_CHECK(cudaMemcpy(tmp.data(), t.ptr, count * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < count; ++i) out[i] = (float)tmp[i];
+  } else {
+    float* d = nullptr;
+    LUMI_CUDA_CHECK(cudaMalloc(&d, count * sizeof(float)));
+    launch_act_to_f32(t.act, d, e->stream);
+    LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    cudaError_t ce = cudaMemcpy(out, d, count * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    LUMI_CUDA_CHECK(ce);
+  }
+  return LUMI_OK;
+  LUMI_API_END(e)
+}
+
+const char* lumi_last_error(lumi_engine* e) { return e ? e->last_error.c_str() : g_create_error.c_str(); }
+
+void lumi_destroy(lumi_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  delete e;
+}
+
+}  // extern "C"

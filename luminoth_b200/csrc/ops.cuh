@@ -1,0 +1,74 @@
+// Launchers for the HBM-bound stages of the path (everything that is not a conv).
+#pragma once
+#include "common.cuh"
+
+namespace lumi {
+
+// ---- format conversion / preprocessing (elementwise.cu)
+void launch_u8_to_act(const uint8_t* img, Act out, const float* means /*3 or nullptr*/, cudaStream_t st);
+void launch_f32_to_act(const float* x, Act out, cudaStream_t st);
+void launch_act_to_f32(Act in, float* y, cudaStream_t st);
+void launch_max_pool(Act in, Act out, int k, int stride, int pad_t, int pad_l, cudaStream_t st);
+void launch_l2norm_scale(Act in, Act out, const float* gamma, float eps, cudaStream_t st);
+void launch_spatial_mean(Act in, Act out, cudaStream_t st);               // (R,h,w,C) -> (R,1,1,C)
+void launch_softmax_rows(const float* x, float* y, int rows, int cols, int in_stride, cudaStream_t st);
+void launch_frcnn_anchors(const int* ref /*A x 4*/, int A, int fh, int fw, int stride, float* out, cudaStream_t st);
+
+// ---- ROI crop + 2x2 max pool (roi.cu) : roi_pool.py:68-95
+// rois [nimg][rmax][4] (x1,y1,x2,y2 px), counts [nimg] (nullptr -> all rmax valid); out (nimg*rmax, ph, pw, C)
+void launch_roi_pool(Act fmap, const float* rois, const int* counts, int rmax, float im_h, float im_w, int ph, int pw,
+                     Act out, cudaStream_t st);
+
+// ---- proposal / detection chains (postproc.cu)
+struct NmsWorkspace {
+  // capacity: problems x cap candidates
+  int problems = 0, cap = 0;
+  float* keys = nullptr;        // [P][cap]   score or -1 (invalid)
+  float* boxes = nullptr;       // [P][cap][4] decoded (+clipped) boxes, input order
+  int* order = nullptr;         // [P][cap]   sorted order (indices into input order)
+  int* nvalid = nullptr;        // [P]        valid candidates (after top-n cut)
+  float* sboxes = nullptr;      // [P][cap][4] boxes in sorted order
+  float* sscores = nullptr;     // [P][cap]
+  unsigned long long* mask = nullptr;  // [P][cap][words]
+  int words = 0;
+  int* keep = nullptr;          // [P][max_out]
+  int* nkeep = nullptr;         // [P]
+  int max_out = 0;
+  unsigned long long* sort_tmp = nullptr;  // global-memory sort scratch for cap > 32768
+};
+void nms_workspace_alloc(NmsWorkspace& ws, int problems, int cap, int max_out);
+void nms_workspace_free(NmsWorkspace& ws);
+
+struct RpnParams {
+  int na;                 // anchors per image
+  float im_h, im_w;
+  int pre_nms_top_n, post_nms_top_n;
+  float nms_threshold, min_prob;
+  int filter_outside, clip_after_nms, apply_nms;
+  int logits;             // 1: cls input holds logits (softmax fused), 0: probabilities
+  int cls_stride, cls_off, box_stride, box_off;  // per-anchor-cell channel layout of the fused head output
+};
+// cls/box: per image [na/A cells][channels]; anchors [na][4] float. Outputs per image [post_nms_top_n].
+void launch_rpn_proposals(const float* cls, const float* box, long img_stride_cls, long img_stride_box, int A,
+                          const float* anchors, int nimg, const RpnParams& p, NmsWorkspace& ws, float* proposals,
+                          float* scores, int* counts, cudaStream_t st);
+
+struct DetParams {
+  int r;                  // rows (proposals / anchors) per image (capacity)
+  int nc;                 // foreground classes
+  float im_h, im_w, var0, var1, min_prob, nms_threshold;
+  int class_max, total_max;
+  int shared_deltas;      // 1: deltas [r][4] shared by all classes (SSD), 0: [r][4*nc]
+  int prob_stride;        // floats between consecutive rows of cls_prob (>= nc+1)
+  int delta_stride;       // floats between consecutive rows of deltas
+};
+// boxes_in [nimg][r][4] (or shared anchors when boxes_img_stride == 0), row_counts [nimg] or nullptr
+void launch_class_detections(const float* boxes_in, long boxes_img_stride, const int* row_counts, const float* deltas,
+                             const float* cls_prob, int nimg, const DetParams& p, NmsWorkspace& ws, float* final_keys,
+                             float* objects, int* labels, float* probs, int* counts, cudaStream_t st);
+
+void launch_sort_desc(const float* scores, int n, int* idx_out, NmsWorkspace& ws, cudaStream_t st);
+void launch_nms_sorted(const float* boxes_sorted, int n, float thr, int max_out, NmsWorkspace& ws, int* keep,
+                       int* nkeep, cudaStream_t st);
+
+}  // namespace lumi

@@ -1,0 +1,512 @@
+// Proposal / detection post-processing chains, batched over (image) or (image, class)
+// "problems":   decode+filter+clip  ->  sort (score desc, ties: lower index)  ->  gather
+//            -> bitmask-matrix NMS (N x ceil(N/64) u64)  ->  serial-scan reduce  ->  gather / top-k.
+//
+// Replaces  luminoth/models/fasterrcnn/rpn_proposal.py:41-197,
+//           luminoth/models/fasterrcnn/rcnn_proposal.py:46-164,
+//           luminoth/models/ssd/proposal.py:41-171,
+//           luminoth/utils/bbox_transform_tf.py:41-99 (decode / clip_boxes)
+// and the TF ops they call (tf.nn.top_k, tf.image.non_max_suppression, tf.boolean_mask).
+// Every float expression keeps the reference's evaluation order with explicit
+// round-to-nearest intrinsics (no FMA contraction): discrete decisions
+// (>=, >, iou > thr) must agree with the fp32 reference bit for bit on equal inputs.
+#include "ops.cuh"
+
+namespace lumi {
+
+// ------------------------------------------------------------------ box arithmetic
+__device__ __forceinline__ float4 decode_box(float4 roi, float dx, float dy, float dw, float dh, float v0, float v1) {
+  const float w = __fadd_rn(__fsub_rn(roi.z, roi.x), 1.f);
+  const float h = __fadd_rn(__fsub_rn(roi.w, roi.y), 1.f);
+  const float urx = __fadd_rn(roi.x, __fmul_rn(.5f, w));
+  const float ury = __fadd_rn(roi.y, __fmul_rn(.5f, h));
+  const float px = __fadd_rn(__fmul_rn(__fmul_rn(dx, w), v0), urx);
+  const float py = __fadd_rn(__fmul_rn(__fmul_rn(dy, h), v0), ury);
+  const float pw = __fmul_rn(expf(__fmul_rn(dw, v1)), w);
+  const float ph = __fmul_rn(expf(__fmul_rn(dh, v1)), h);
+  float4 o;
+  o.x = __fsub_rn(px, __fmul_rn(.5f, pw));
+  o.y = __fsub_rn(py, __fmul_rn(.5f, ph));
+  o.z = __fsub_rn(__fadd_rn(px, __fmul_rn(.5f, pw)), 1.f);   // "-1. extra" (bbox_transform_tf.py:59-61)
+  o.w = __fsub_rn(__fadd_rn(py, __fmul_rn(.5f, ph)), 1.f);
+  return o;
+}
+__device__ __forceinline__ float4 clip_box(float4 b, float im_h, float im_w) {
+  const float mw = __fsub_rn(im_w, 1.f), mh = __fsub_rn(im_h, 1.f);
+  b.x = fmaxf(fminf(b.x, mw), 0.f);
+  b.z = fmaxf(fminf(b.z, mw), 0.f);
+  b.y = fmaxf(fminf(b.y, mh), 0.f);
+  b.w = fmaxf(fminf(b.w, mh), 0.f);
+  return b;
+}
+__device__ __forceinline__ bool area_positive(float4 b) {
+  return __fmul_rn(fmaxf(__fsub_rn(b.z, b.x), 0.f), fmaxf(__fsub_rn(b.w, b.y), 0.f)) > 0.f;
+}
+// tf.image.non_max_suppression's IoU test on (x1,y1,x2,y2) boxes.
+__device__ __forceinline__ bool iou_gt(float4 a, float4 b, float thr) {
+  const float ymin_i = fminf(a.y, a.w), xmin_i = fminf(a.x, a.z), ymax_i = fmaxf(a.y, a.w), xmax_i = fmaxf(a.x, a.z);
+  const float ymin_j = fminf(b.y, b.w), xmin_j = fminf(b.x, b.z), ymax_j = fmaxf(b.y, b.w), xmax_j = fmaxf(b.x, b.z);
+  const float area_i = __fmul_rn(__fsub_rn(ymax_i, ymin_i), __fsub_rn(xmax_i, xmin_i));
+  const float area_j = __fmul_rn(__fsub_rn(ymax_j, ymin_j), __fsub_rn(xmax_j, xmin_j));
+  if (area_i <= 0.f || area_j <= 0.f) return false;
+  const float iy0 = fmaxf(ymin_i, ymin_j), ix0 = fmaxf(xmin_i, xmin_j);
+  const float iy1 = fminf(ymax_i, ymax_j), ix1 = fminf(xmax_i, xmax_j);
+  const float inter = __fmul_rn(fmaxf(__fsub_rn(iy1, iy0), 0.f), fmaxf(__fsub_rn(ix1, ix0), 0.f));
+  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
+  return iou > thr;
+}
+
+// ------------------------------------------------------------------ workspace
+void nms_workspace_alloc(NmsWorkspace& ws, int problems, int cap, int max_out) {
+  ws.problems = problems; ws.cap = cap; ws.max_out = max_out;
+  ws.words = cdiv(cap, 64);
+  size_t pc = (size_t)problems * cap;
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.keys, pc * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.boxes, pc * 4 * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.order, pc * sizeof(int)));
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.nvalid, problems * sizeof(int)));
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.sboxes, pc * 4 * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.sscores, pc * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.mask, pc * ws.words * sizeof(unsigned long long)));
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.keep, (size_t)problems * max_out * sizeof(int)));
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.nkeep, problems * sizeof(int)));
+  int p2 = 1; while (p2 < cap) p2 <<= 1;
+  if (p2 > 32768) LUMI_CUDA_CHECK(cudaMalloc(&ws.sort_tmp, (size_t)problems * p2 * sizeof(unsigned long long)));
+}
+void nms_workspace_free(NmsWorkspace& ws) {
+  cudaFree(ws.keys); cudaFree(ws.boxes); cudaFree(ws.order); cudaFree(ws.nvalid); cudaFree(ws.sboxes);
+  cudaFree(ws.sscores); cudaFree(ws.mask); cudaFree(ws.keep); cudaFree(ws.nkeep); cudaFree(ws.sort_tmp);
+  ws = NmsWorkspace();
+}
+
+// ------------------------------------------------------------------ sort (one CTA per problem)
+// key' = bits(score)+1 for valid (score >= 0), 0 for invalid / padding; order: key' desc, index asc.
+__device__ __forceinline__ uint32_t score_key(float s) { return (s >= 0.f) ? (__float_as_uint(s) + 1u) : 0u; }
+
+template <typename IdxT>
+__global__ void __launch_bounds__(1024) sort_desc_smem_kernel(const float* __restrict__ keys, int cap, int cap_p2,
+                                                              const int* __restrict__ n_in, int topn,
+                                                              int* __restrict__ order, int* __restrict__ nvalid) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint32_t* k = reinterpret_cast<uint32_t*>(sm);
+  IdxT* ix = reinterpret_cast<IdxT*>(sm + (size_t)cap_p2 * 4);
+  __shared__ int s_count;
+  const int p = blockIdx.x;
+  const int n = n_in ? min(n_in[p], cap) : cap;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < cap_p2; i += blockDim.x) {
+    uint32_t key = 0;
+    if (i < n) key = score_key(keys[(size_t)p * cap + i]);
+    k[i] = key; ix[i] = (IdxT)i;
+    local += key != 0;
+  }
+  atomicAdd(&s_count, local);
+  for (int size = 2; size <= cap_p2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (cap_p2 >> 1); t += blockDim.x) {
+        const int i = 2 * t - (t & (stride - 1));
+        const int j = i + stride;
+        const uint32_t ki = k[i], kj = k[j];
+        const IdxT ii = ix[i], ij = ix[j];
+        const bool i_first = (ki > kj) || (ki == kj && ii < ij);
+        const bool want_i_first = ((i & size) == 0);
+        if (i_first != want_i_first) { k[i] = kj; k[j] = ki; ix[i] = ij; ix[j] = ii; }
+      }
+    }
+  }
+  __syncthreads();
+  const int nv = min(s_count, topn);
+  if (threadIdx.x == 0) nvalid[p] = nv;
+  for (int r = threadIdx.x; r < nv; r += blockDim.x) order[(size_t)p * cap + r] = (int)ix[r];
+}
+
+// global-memory fallback for more than 32768 candidates per problem (large images)
+__global__ void __launch_bounds__(1024) sort_desc_gmem_kernel(const float* __restrict__ keys, int cap, int cap_p2,
+                                                              const int* __restrict__ n_in, int topn,
+                                                              unsigned long long* __restrict__ tmp,
+                                                              int* __restrict__ order, int* __restrict__ nvalid) {
+  __shared__ int s_count;
+  const int p = blockIdx.x;
+  const int n = n_in ? min(n_in[p], cap) : cap;
+  unsigned long long* v = tmp + (size_t)p * cap_p2;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < cap_p2; i += blockDim.x) {
+    uint32_t key = 0;
+    if (i < n) key = score_key(keys[(size_t)p * cap + i]);
+    v[i] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+    local += key != 0;
+  }
+  atomicAdd(&s_count, local);
+  for (int size = 2; size <= cap_p2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (cap_p2 >> 1); t += blockDim.x) {
+        const int i = 2 * t - (t & (stride - 1));
+        const int j = i + stride;
+        const unsigned long long a = v[i], b = v[j];
+        const bool i_first = a > b;
+        const bool want_i_first = ((i & size) == 0);
+        if (i_first != want_i_first) { v[i] = b; v[j] = a; }
+      }
+    }
+  }
+  __syncthreads();
+  const int nv = min(s_count, topn);
+  if (threadIdx.x == 0) nvalid[p] = nv;
+  for (int r = threadIdx.x; r < nv; r += blockDim.x)
+    order[(size_t)p * cap + r] = (int)(0xFFFFFFFFu - (uint32_t)(v[r] & 0xFFFFFFFFull));
+}
+
+static void run_sort(const float* keys, int problems, int cap, const int* n_in, int topn, int* order, int* nvalid,
+                     unsigned long long* tmp, cudaStream_t st) {
+  if (!problems || !cap) return;
+  int p2 = 2;
+  while (p2 < cap) p2 <<= 1;
+  if (p2 <= 16384) {
+    size_t smem = (size_t)p2 * 8;
+    static bool set32 = false;
+    if (!set32) {
+      LUMI_CUDA_CHECK(cudaFuncSetAttribute(sort_desc_smem_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           16384 * 8));
+      set32 = true;
+    }
+    int threads = p2 / 2 < 1024 ? (p2 / 2 < 32 ? 32 : p2 / 2) : 1024;
+    sort_desc_smem_kernel<uint32_t><<<problems, threads, smem, st>>>(keys, cap, p2, n_in, topn, order, nvalid);
+  } else if (p2 <= 32768) {
+    size_t smem = (size_t)p2 * 6;
+    static bool set16 = false;
+    if (!set16) {
+      LUMI_CUDA_CHECK(cudaFuncSetAttribute(sort_desc_smem_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           32768 * 6));
+      set16 = true;
+    }
+    sort_desc_smem_kernel<uint16_t><<<problems, 1024, smem, st>>>(keys, cap, p2, n_in, topn, order, nvalid);
+  } else {
+    LUMI_REQUIRE(tmp != nullptr, "sort: no global scratch for > 32768 candidates");
+    sort_desc_gmem_kernel<<<problems, 1024, 0, st>>>(keys, cap, p2, n_in, topn, tmp, order, nvalid);
+  }
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ gather sorted
+__global__ void gather_sorted_kernel(const float* __restrict__ boxes, const float* __restrict__ keys,
+                                     const int* __restrict__ order, const int* __restrict__ nvalid, int cap,
+                                     float* __restrict__ sboxes, float* __restrict__ sscores) {
+  const int p = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nvalid[p]) return;
+  const size_t src = (size_t)p * cap + order[(size_t)p * cap + r];
+  const size_t dst = (size_t)p * cap + r;
+  reinterpret_cast<float4*>(sboxes)[dst] = reinterpret_cast<const float4*>(boxes)[src];
+  sscores[dst] = keys[src];
+}
+
+// ------------------------------------------------------------------ NMS bitmask matrix
+// grid (pair slot, problem); 64 threads; a block walks the upper-triangle (row block, col block) pairs
+// of its problem with a grid stride, so launch cost follows the live candidate count, not the capacity.
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sboxes, const int* __restrict__ nvalid,
+                                                      int cap, int words, float thr,
+                                                      unsigned long long* __restrict__ mask) {
+  const int p = blockIdx.y;
+  const int n = nvalid[p];
+  const int nw = (n + 63) >> 6;
+  const long npairs = (long)nw * (nw + 1) / 2;
+  __shared__ float4 cbox[64];
+  const float4* B = reinterpret_cast<const float4*>(sboxes) + (size_t)p * cap;
+  const int t = threadIdx.x;
+  for (long pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+    // pair index -> (rb, cb >= rb); row rb starts at rb*(2nw-rb+1)/2
+    const double disc = (2.0 * nw + 1.0) * (2.0 * nw + 1.0) - 8.0 * (double)pr;
+    int rb = (int)(((2.0 * nw + 1.0) - sqrt(disc)) * 0.5);
+    if (rb < 0) rb = 0;
+    if (rb > nw - 1) rb = nw - 1;
+    while ((long)rb * (2 * nw - rb + 1) / 2 > pr) --rb;
+    while ((long)(rb + 1) * (2 * nw - rb) / 2 <= pr) ++rb;
+    const int cb = rb + (int)(pr - (long)rb * (2 * nw - rb + 1) / 2);
+    __syncthreads();
+    if (cb * 64 + t < n) cbox[t] = B[cb * 64 + t];
+    __syncthreads();
+    const int i = rb * 64 + t;
+    if (i >= n) continue;
+    const float4 bi = B[i];
+    unsigned long long bits = 0ull;
+    const int jmax = min(64, n - cb * 64);
+    for (int j = 0; j < jmax; ++j) {
+      const int col = cb * 64 + j;
+      if (col > i && iou_gt(bi, cbox[j], thr)) bits |= 1ull << j;
+    }
+    mask[((size_t)p * cap + i) * words + cb] = bits;
+  }
+}
+
+// serial-scan reduce: one CTA per problem walks 64-box chunks in score order.
+__global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long* __restrict__ mask,
+                                                       const int* __restrict__ nvalid, int cap, int words,
+                                                       int max_out, int* __restrict__ keep, int* __restrict__ nkeep) {
+  extern __shared__ unsigned long long removed[];     // [words]
+  __shared__ unsigned long long diag[64];
+  __shared__ int s_kept[64];
+  __shared__ int s_nk, s_total, s_done;
+  const int p = blockIdx.x;
+  const int n = nvalid[p];
+  const int nw = (n + 63) >> 6;
+  const unsigned long long* M = mask + (size_t)p * cap * words;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = 0ull;
+  if (threadIdx.x == 0) { s_total = 0; s_done = (max_out <= 0 || n == 0) ? 1 : 0; }
+  __syncthreads();
+  for (int c = 0; c < nw && !s_done; ++c) {
+    if (threadIdx.x < 64) {
+      const int row = c * 64 + threadIdx.x;
+      diag[threadIdx.x] = row < n ? M[(size_t)row * words + c] : 0ull;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long cur = removed[c];
+      int nk = 0, total = s_total;
+      const int lim = min(64, n - c * 64);
+      for (int b = 0; b < lim; ++b) {
+        if (!((cur >> b) & 1ull)) {
+          s_kept[nk++] = b;
+          keep[(size_t)p * max_out + total] = c * 64 + b;
+          ++total;
+          if (total >= max_out) { s_done = 1; break; }
+          cur |= diag[b];
+        }
+      }
+      s_nk = nk; s_total = total;
+    }
+    __syncthreads();
+    if (s_done) break;
+    const int nk = s_nk;
+    for (int w = c + 1 + threadIdx.x; w < nw; w += blockDim.x) {
+      unsigned long long acc = removed[w];
+      for (int i = 0; i < nk; ++i) acc |= M[(size_t)(c * 64 + s_kept[i]) * words + w];
+      removed[w] = acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) nkeep[p] = s_total;
+}
+
+static void run_nms(NmsWorkspace& ws, int problems, float thr, int max_out, cudaStream_t st) {
+  if (!problems) return;
+  long maxpairs = (long)ws.words * (ws.words + 1) / 2;
+  dim3 grid((unsigned)(maxpairs < 2048 ? maxpairs : 2048), problems);
+  nms_mask_kernel<<<grid, 64, 0, st>>>(ws.sboxes, ws.nvalid, ws.cap, ws.words, thr, ws.mask);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+  size_t smem = (size_t)ws.words * sizeof(unsigned long long);
+  nms_scan_kernel<<<problems, 256, smem, st>>>(ws.mask, ws.nvalid, ws.cap, ws.words, max_out, ws.keep, ws.nkeep);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ RPN chain
+__global__ void rpn_decode_kernel(const float* __restrict__ cls, const float* __restrict__ box, long img_stride_cls,
+                                  long img_stride_box, int A, const float* __restrict__ anchors, RpnParams p, int cap,
+                                  float* __restrict__ keys, float* __restrict__ boxes) {
+  const int img = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.na) return;
+  const int cell = i / A, a = i % A;
+  const float* cp = cls + (size_t)img * img_stride_cls + (size_t)cell * p.cls_stride + p.cls_off + 2 * a;
+  const float* bp = box + (size_t)img * img_stride_box + (size_t)cell * p.box_stride + p.box_off + 4 * a;
+  float score;
+  if (p.logits) {          // rpn.py:160-163: reshape(-1,2) softmax, foreground = column 1
+    const float s0 = cp[0], s1 = cp[1];
+    const float m = fmaxf(s0, s1);
+    const float e0 = expf(__fsub_rn(s0, m)), e1 = expf(__fsub_rn(s1, m));
+    score = __fdiv_rn(e1, __fadd_rn(e0, e1));
+  } else {
+    score = cp[1];
+  }
+  const float4 an = reinterpret_cast<const float4*>(anchors)[i];
+  float4 b = decode_box(an, bp[0], bp[1], bp[2], bp[3], 1.f, 1.f);
+  bool ok = (score >= p.min_prob) && area_positive(b);
+  if (p.filter_outside) ok = ok && (an.x >= 0.f && an.y >= 0.f && an.z < p.im_w && an.w < p.im_h);
+  if (!p.clip_after_nms) b = clip_box(b, p.im_h, p.im_w);
+  const size_t o = (size_t)img * cap + i;
+  keys[o] = ok ? score : -1.f;
+  reinterpret_cast<float4*>(boxes)[o] = b;
+}
+
+__global__ void rpn_output_kernel(const float* __restrict__ sboxes, const float* __restrict__ sscores,
+                                  const int* __restrict__ keep, const int* __restrict__ nkeep, int cap, int max_out,
+                                  int clip, float im_h, float im_w, float* __restrict__ proposals,
+                                  float* __restrict__ scores, int* __restrict__ counts) {
+  const int img = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nk = nkeep[img];
+  if (j == 0) counts[img] = nk;
+  if (j >= max_out) return;
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  float s = 0.f;
+  if (j < nk) {
+    const size_t src = (size_t)img * cap + keep[(size_t)img * max_out + j];
+    b = reinterpret_cast<const float4*>(sboxes)[src];
+    s = sscores[src];
+    if (clip) b = clip_box(b, im_h, im_w);
+  }
+  reinterpret_cast<float4*>(proposals)[(size_t)img * max_out + j] = b;
+  scores[(size_t)img * max_out + j] = s;
+}
+
+void launch_rpn_proposals(const float* cls, const float* box, long img_stride_cls, long img_stride_box, int A,
+                          const float* anchors, int nimg, const RpnParams& p, NmsWorkspace& ws, float* proposals,
+                          float* scores, int* counts, cudaStream_t st) {
+  LUMI_REQUIRE(p.na <= ws.cap && nimg <= ws.problems, "rpn_proposals: workspace too small");
+  if (!nimg || !p.na) return;
+  dim3 g1(cdiv(p.na, 256), nimg);
+  rpn_decode_kernel<<<g1, 256, 0, st>>>(cls, box, img_stride_cls, img_stride_box, A, anchors, p, ws.cap, ws.keys,
+                                        ws.boxes);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+  // problem stride is ws.cap; candidates per problem p.na: fill the tail with invalid once if na < cap
+  if (p.na < ws.cap) {
+    LUMI_CUDA_CHECK(cudaMemset2DAsync(ws.keys + p.na, (size_t)ws.cap * sizeof(float), 0xFF,
+                                      (size_t)(ws.cap - p.na) * sizeof(float), nimg, st));   // 0xFFFFFFFF = NaN -> invalid
+  }
+  run_sort(ws.keys, nimg, ws.cap, nullptr, p.pre_nms_top_n, ws.order, ws.nvalid, ws.sort_tmp, st);
+  dim3 g2(cdiv(ws.cap, 256), nimg);
+  gather_sorted_kernel<<<g2, 256, 0, st>>>(ws.boxes, ws.keys, ws.order, ws.nvalid, ws.cap, ws.sboxes, ws.sscores);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+  const float thr = p.apply_nms ? p.nms_threshold : INFINITY;
+  LUMI_REQUIRE(p.post_nms_top_n <= ws.max_out, "rpn_proposals: post_nms_top_n exceeds workspace");
+  run_nms(ws, nimg, thr, p.post_nms_top_n, st);
+  dim3 g3(cdiv(p.post_nms_top_n, 256), nimg);
+  rpn_output_kernel<<<g3, 256, 0, st>>>(ws.sboxes, ws.sscores, ws.keep, ws.nkeep, ws.cap, p.post_nms_top_n,
+                                        p.clip_after_nms, p.im_h, p.im_w, proposals, scores, counts);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ per-class detection chain
+__global__ void det_decode_kernel(const float* __restrict__ boxes_in, long boxes_img_stride,
+                                  const int* __restrict__ row_counts, const float* __restrict__ deltas,
+                                  const float* __restrict__ cls_prob, DetParams p, int cap, float* __restrict__ keys,
+                                  float* __restrict__ boxes) {
+  const int prob_id = blockIdx.y;               // img*nc + c
+  const int img = prob_id / p.nc, c = prob_id % p.nc;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.r) return;
+  const size_t o = (size_t)prob_id * cap + r;
+  const bool live = row_counts == nullptr || r < row_counts[img];
+  if (!live) { keys[o] = -1.f; return; }
+  const size_t row = (size_t)img * p.r + r;
+  const float prob = cls_prob[row * p.prob_stride + c + 1];
+  const float* dp = deltas + row * p.delta_stride + (p.shared_deltas ? 0 : 4 * c);
+  const float4 bin = reinterpret_cast<const float4*>(boxes_in)[(size_t)img * (boxes_img_stride / 4) + r];
+  float4 b = decode_box(bin, dp[0], dp[1], dp[2], dp[3], p.var0, p.var1);
+  b = clip_box(b, p.im_h, p.im_w);
+  const bool ok = (prob >= p.min_prob) && area_positive(b);
+  keys[o] = ok ? prob : -1.f;
+  reinterpret_cast<float4*>(boxes)[o] = b;
+}
+
+// concat per-class selections (class-major, NMS selection order) as sparse keys [img][nc*class_max]
+__global__ void det_concat_kernel(const float* __restrict__ sscores, const int* __restrict__ keep,
+                                  const int* __restrict__ nkeep, int nc, int cap, int class_max,
+                                  float* __restrict__ fkeys) {
+  const int prob_id = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= class_max) return;
+  const int img = prob_id / nc, c = prob_id % nc;
+  float v = -1.f;
+  if (j < nkeep[prob_id]) v = sscores[(size_t)prob_id * cap + keep[(size_t)prob_id * class_max + j]];
+  fkeys[((size_t)img * nc + c) * class_max + j] = v;
+}
+
+__global__ void det_output_kernel(const float* __restrict__ sboxes, const float* __restrict__ sscores,
+                                  const int* __restrict__ keep, const int* __restrict__ forder,
+                                  const int* __restrict__ fnvalid, int nc, int cap, int class_max, int total_max,
+                                  float* __restrict__ objects, int* __restrict__ labels, float* __restrict__ probs,
+                                  int* __restrict__ counts) {
+  const int img = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nv = fnvalid[img];
+  if (k == 0) counts[img] = nv;
+  if (k >= total_max) return;
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  float s = 0.f;
+  int lab = -1;
+  if (k < nv) {
+    const int idx = forder[(size_t)img * nc * class_max + k];
+    const int c = idx / class_max, j = idx % class_max;
+    const int prob_id = img * nc + c;
+    const size_t src = (size_t)prob_id * cap + keep[(size_t)prob_id * class_max + j];
+    b = reinterpret_cast<const float4*>(sboxes)[src];
+    s = sscores[src];
+    lab = c;
+  }
+  reinterpret_cast<float4*>(objects)[(size_t)img * total_max + k] = b;
+  probs[(size_t)img * total_max + k] = s;
+  labels[(size_t)img * total_max + k] = lab;
+}
+
+// final_keys: scratch [nimg][nc*class_max] floats followed by int order [same] and int nvalid[nimg]
+void launch_class_detections(const float* boxes_in, long boxes_img_stride, const int* row_counts, const float* deltas,
+                             const float* cls_prob, int nimg, const DetParams& p, NmsWorkspace& ws, float* final_keys,
+                             float* objects, int* labels, float* probs, int* counts, cudaStream_t st) {
+  const int P = nimg * p.nc;
+  LUMI_REQUIRE(P <= ws.problems && p.r <= ws.cap && p.class_max == ws.max_out, "class_detections: workspace mismatch");
+  if (!P || !p.r) return;
+  dim3 g1(cdiv(p.r, 256), P);
+  det_decode_kernel<<<g1, 256, 0, st>>>(boxes_in, boxes_img_stride, row_counts, deltas, cls_prob, p, ws.cap, ws.keys,
+                                        ws.boxes);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+  if (p.r < ws.cap)
+    LUMI_CUDA_CHECK(cudaMemset2DAsync(ws.keys + p.r, (size_t)ws.cap * sizeof(float), 0xFF,
+                                      (size_t)(ws.cap - p.r) * sizeof(float), P, st));
+  run_sort(ws.keys, P, ws.cap, nullptr, ws.cap, ws.order, ws.nvalid, ws.sort_tmp, st);
+  dim3 g2(cdiv(ws.cap, 256), P);
+  gather_sorted_kernel<<<g2, 256, 0, st>>>(ws.boxes, ws.keys, ws.order, ws.nvalid, ws.cap, ws.sboxes, ws.sscores);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+  run_nms(ws, P, p.nms_threshold, p.class_max, st);
+  const int fcap = p.nc * p.class_max;
+  float* fkeys = final_keys;
+  int* forder = reinterpret_cast<int*>(final_keys + (size_t)nimg * fcap);
+  int* fnvalid = forder + (size_t)nimg * fcap;
+  dim3 g3(cdiv(p.class_max, 128), P);
+  det_concat_kernel<<<g3, 128, 0, st>>>(ws.sscores, ws.keep, ws.nkeep, p.nc, ws.cap, p.class_max, fkeys);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+  run_sort(fkeys, nimg, fcap, nullptr, p.total_max, forder, fnvalid, nullptr, st);
+  dim3 g4(cdiv(p.total_max, 128), nimg);
+  det_output_kernel<<<g4, 128, 0, st>>>(ws.sboxes, ws.sscores, ws.keep, forder, fnvalid, p.nc, ws.cap, p.class_max,
+                                        p.total_max, objects, labels, probs, counts);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ stand-alone sort / NMS
+void launch_sort_desc(const float* scores, int n, int* idx_out, NmsWorkspace& ws, cudaStream_t st) {
+  LUMI_REQUIRE(n <= ws.cap && ws.problems >= 1, "sort_desc: workspace too small");
+  LUMI_CUDA_CHECK(cudaMemsetAsync(ws.keys, 0xFF, (size_t)ws.cap * sizeof(float), st));
+  LUMI_CUDA_CHECK(cudaMemcpyAsync(ws.keys, scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  run_sort(ws.keys, 1, ws.cap, nullptr, ws.cap, ws.order, ws.nvalid, ws.sort_tmp, st);
+  LUMI_CUDA_CHECK(cudaMemcpyAsync(idx_out, ws.order, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+void launch_nms_sorted(const float* boxes_sorted, int n, float thr, int max_out, NmsWorkspace& ws, int* keep,
+                       int* nkeep, cudaStream_t st) {
+  LUMI_REQUIRE(n <= ws.cap && max_out <= ws.max_out, "nms_sorted: workspace too small");
+  LUMI_CUDA_CHECK(cudaMemcpyAsync(ws.sboxes, boxes_sorted, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  set_int_kernel<<<1, 1, 0, st>>>(ws.nvalid, n);
+  count_launch();
+  run_nms(ws, 1, thr, max_out, st);
+  LUMI_CUDA_CHECK(cudaMemcpyAsync(keep, ws.keep, (size_t)max_out * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  LUMI_CUDA_CHECK(cudaMemcpyAsync(nkeep, ws.nkeep, sizeof(int), cudaMemcpyDeviceToDevice, st));
+}
+
+}  // namespace lumi

@@ -1,0 +1,252 @@
+"""ctypes binding of libluminoth_b200.so (the C ABI in include/luminoth_b200.h).
+
+Thin by design: torch tensors / numpy arrays are only the containers whose
+pointers cross the boundary.  There is NO CPU fallback: if the library cannot
+be loaded, or no CUDA device is visible, every entry point raises.
+"""
+import ctypes
+import json
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libluminoth_b200.so')
+
+LUMI_OK, LUMI_EINVAL, LUMI_ECUDA, LUMI_ESTATE, LUMI_ENOWEIGHT, LUMI_EOVERFLOW = 0, -1, -2, -3, -4, -5
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_c_f_p = ctypes.POINTER(ctypes.c_float)
+_c_i64_p = ctypes.POINTER(ctypes.c_int64)
+_c_i32_p = ctypes.POINTER(ctypes.c_int32)
+
+# name -> (restype, argtypes); must list every symbol include/luminoth_b200.h declares
+SIGNATURES = {
+    'lumi_version': (ctypes.c_char_p, []),
+    'lumi_device_count': (ctypes.c_int, []),
+    'lumi_create': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                   ctypes.POINTER(ctypes.c_void_p)]),
+    'lumi_set_weight': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, _c_i64_p, ctypes.c_int]),
+    'lumi_num_weights': (ctypes.c_int, [ctypes.c_void_p]),
+    'lumi_weight_info': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), _c_i64_p,
+                                        _c_int_p]),
+    'lumi_finalize': (ctypes.c_int, [ctypes.c_void_p]),
+    'lumi_predict': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_int]),
+    'lumi_max_detections': (ctypes.c_int, [ctypes.c_void_p]),
+    'lumi_stream': (ctypes.c_void_p, [ctypes.c_void_p]),
+    'lumi_synchronize': (ctypes.c_int, [ctypes.c_void_p]),
+    'lumi_last_launch_count': (ctypes.c_int, [ctypes.c_void_p]),
+    'lumi_set_conv_impl': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    'lumi_get_tensor': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, _c_i64_p,
+                                       _c_i64_p]),
+    'lumi_last_error': (ctypes.c_char_p, [ctypes.c_void_p]),
+    'lumi_destroy': (None, [ctypes.c_void_p]),
+    'lumi_op_last_error': (ctypes.c_char_p, []),
+    'lumi_op_conv2d': (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] + [ctypes.c_int] * 6 +
+                       [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2 + [ctypes.c_void_p, _c_int_p, _c_int_p,
+                                                                      ctypes.c_void_p]),
+    'lumi_op_max_pool': (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_void_p]),
+    'lumi_op_roi_pool': (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p,
+                                                                                ctypes.c_int, ctypes.c_float,
+                                                                                ctypes.c_float, ctypes.c_int,
+                                                                                ctypes.c_int, ctypes.c_void_p,
+                                                                                ctypes.c_void_p]),
+    'lumi_op_sort_desc': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    'lumi_op_nms_sorted': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
+    'lumi_op_rpn_proposals': (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                                                     ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                                                     ctypes.c_float, ctypes.c_int, ctypes.c_int] +
+                              [ctypes.c_void_p] * 4),
+    'lumi_op_class_detections': (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_int] +
+                                 [ctypes.c_float] * 6 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5),
+}
+
+
+def load_library():
+    """Load (once) and type the C ABI.  Raises RuntimeError when the library is
+    missing -- it is never silently replaced by a CPU path."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'luminoth_b200: %s is not built (run `python -c "import __graft_entry__ as g; g.build()"`); '
+                'there is no CPU fallback' % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def _raise(code, msg):
+    msg = msg.decode() if isinstance(msg, bytes) else str(msg)
+    if code in (LUMI_EINVAL, LUMI_ENOWEIGHT):
+        raise ValueError(msg)
+    raise RuntimeError('luminoth_b200 (code %d): %s' % (code, msg))
+
+
+def _to_plain(config):
+    if isinstance(config, dict):
+        return {k: _to_plain(v) for k, v in config.items()}
+    if isinstance(config, (list, tuple)):
+        return [_to_plain(v) for v in config]
+    if isinstance(config, np.generic):
+        return config.item()
+    return config
+
+
+class Engine(object):
+    """One engine handle = one GPU, one stream, one workspace.  Not re-entrant:
+    calls are serialised by a lock (the reference has a single tf.Session)."""
+
+    def __init__(self, config, device=0, max_batch=1, max_h=None, max_w=None):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        self._lock = threading.Lock()
+        mtype = config['model']['type']
+        if max_h is None or max_w is None:
+            ip = config['dataset']['image_preprocessing']
+            if mtype == 'ssd':
+                max_h, max_w = ip['fixed_height'], ip['fixed_width']
+            else:
+                side = max(int(ip.get('max_size') or 1024), int(ip.get('min_size') or 600))
+                max_h = max_w = side
+        cfg_json = json.dumps(_to_plain(config)).encode()
+        rc = self._lib.lumi_create(cfg_json, int(device), int(max_batch), int(max_h), int(max_w),
+                                   ctypes.byref(self._h))
+        if rc != LUMI_OK:
+            _raise(rc, self._lib.lumi_last_error(None))
+        self.device = int(device)
+        self.max_batch = int(max_batch)
+        self.max_detections = self._lib.lumi_max_detections(self._h)
+        self._finalized = False
+
+    # ---- weights
+    def weight_specs(self):
+        out = []
+        name = ctypes.c_char_p()
+        shape = (ctypes.c_int64 * 4)()
+        ndim = ctypes.c_int()
+        for i in range(self._lib.lumi_num_weights(self._h)):
+            self._lib.lumi_weight_info(self._h, i, ctypes.byref(name), shape, ctypes.byref(ndim))
+            out.append((name.value.decode(), tuple(int(shape[j]) for j in range(ndim.value))))
+        return out
+
+    def set_weight(self, name, array):
+        a = np.ascontiguousarray(array, dtype=np.float32)
+        shape = (ctypes.c_int64 * a.ndim)(*a.shape)
+        rc = self._lib.lumi_set_weight(self._h, name.encode(), a.ctypes.data_as(ctypes.c_void_p), shape, a.ndim)
+        if rc != LUMI_OK:
+            _raise(rc, self._lib.lumi_last_error(self._h))
+
+    def load_weights(self, weights):
+        for name, shape in self.weight_specs():
+            if name not in weights:
+                raise ValueError("variable '%s' missing from the weight dict" % name)
+            self.set_weight(name, weights[name])
+        return self
+
+    def finalize(self):
+        rc = self._lib.lumi_finalize(self._h)
+        if rc != LUMI_OK:
+            _raise(rc, self._lib.lumi_last_error(self._h))
+        self._finalized = True
+        return self
+
+    def set_conv_impl(self, impl):
+        rc = self._lib.lumi_set_conv_impl(self._h, {'simt': 0, 'tc': 1}.get(impl, impl))
+        if rc != LUMI_OK:
+            raise ValueError('conv impl must be "simt" or "tc"')
+
+    # ---- forward
+    def predict_raw(self, images):
+        """images: uint8 array [n,h,w,3] (numpy -> host path, H2D inside the
+        call; CUDA torch tensor -> device path).  Returns numpy
+        (boxes [n,K,4], scores [n,K], labels [n,K], counts [n])."""
+        on_dev = False
+        if isinstance(images, np.ndarray):
+            imgs = np.ascontiguousarray(images, dtype=np.uint8)
+            n, h, w, c = imgs.shape
+            ptr = imgs.ctypes.data
+        else:                       # torch tensor
+            import torch
+            assert images.dtype == torch.uint8 and images.is_contiguous()
+            n, h, w, c = images.shape
+            on_dev = images.is_cuda
+            ptr = images.data_ptr()
+        if c != 3:
+            raise ValueError('images must be [n,h,w,3] RGB uint8')
+        k = self.max_detections
+        boxes = np.empty((n, k, 4), np.float32)
+        scores = np.empty((n, k), np.float32)
+        labels = np.empty((n, k), np.int32)
+        counts = np.empty((n,), np.int32)
+        with self._lock:
+            rc = self._lib.lumi_predict(self._h, ctypes.c_void_p(ptr), int(on_dev), n, h, w,
+                                        boxes.ctypes.data_as(ctypes.c_void_p), scores.ctypes.data_as(ctypes.c_void_p),
+                                        labels.ctypes.data_as(ctypes.c_void_p), counts.ctypes.data_as(ctypes.c_void_p), 0)
+            if rc != LUMI_OK:
+                _raise(rc, self._lib.lumi_last_error(self._h))
+        return boxes, scores, labels, counts
+
+    def predict_device(self, images, boxes, scores, labels, counts):
+        """Fully asynchronous device-resident call (CUDA torch tensors in and out)."""
+        n, h, w, _ = images.shape
+        with self._lock:
+            rc = self._lib.lumi_predict(self._h, ctypes.c_void_p(images.data_ptr()), 1, n, h, w,
+                                        ctypes.c_void_p(boxes.data_ptr()), ctypes.c_void_p(scores.data_ptr()),
+                                        ctypes.c_void_p(labels.data_ptr()), ctypes.c_void_p(counts.data_ptr()), 1)
+            if rc != LUMI_OK:
+                _raise(rc, self._lib.lumi_last_error(self._h))
+
+    def synchronize(self):
+        rc = self._lib.lumi_synchronize(self._h)
+        if rc != LUMI_OK:
+            _raise(rc, self._lib.lumi_last_error(self._h))
+
+    @property
+    def stream(self):
+        return self._lib.lumi_stream(self._h)
+
+    @property
+    def last_launch_count(self):
+        return self._lib.lumi_last_launch_count(self._h)
+
+    def get_tensor(self, name):
+        numel = ctypes.c_int64()
+        shape = (ctypes.c_int64 * 4)()
+        with self._lock:
+            rc = self._lib.lumi_get_tensor(self._h, name.encode(), None, 0, ctypes.byref(numel), shape)
+            if rc != LUMI_OK:
+                _raise(rc, self._lib.lumi_last_error(self._h))
+            out = np.empty((numel.value,), np.float32)
+            rc = self._lib.lumi_get_tensor(self._h, name.encode(), out.ctypes.data_as(ctypes.c_void_p), numel.value,
+                                           ctypes.byref(numel), shape)
+            if rc != LUMI_OK:
+                _raise(rc, self._lib.lumi_last_error(self._h))
+        shp = [int(s) for s in shape]
+        while len(shp) > 1 and shp[-1] == 1:
+            shp.pop()
+        return out.reshape(shp)
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h:
+            self._lib.lumi_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
