@@ -73,6 +73,12 @@ int lumi_synchronize(lumi_engine* e);
 /* Kernels launched by the last lumi_predict (our own kernels, for bench.py's gpu_launches). */
 int lumi_last_launch_count(lumi_engine* e);
 
+/* Per-category device timing (CUDA events on the engine stream around our kernels; bench.py's roofline).
+ * lumi_profile_read drains the spans recorded since the last read: "name:spans:total_ms:work;..."
+ * (work = algorithmic FLOPs for conv_*, algorithmic bytes for roi_pool). */
+int lumi_profile_enable(lumi_engine* e, int enable);
+const char* lumi_profile_read(lumi_engine* e);
+
 /* Choose the convolution implementation: 0 = fp32 SIMT implicit GEMM everywhere,
  * 1 = tcgen05 fp16x2-split tensor-core kernel wherever the layer qualifies (default). */
 int lumi_set_conv_impl(lumi_engine* e, int impl);

@@ -210,13 +210,21 @@ struct TcArgs {
 };
 
 constexpr int TC_A_BYTES = 128 * 128;       // 128 pixel rows x 64 fp16 (one 128 B swizzle row each)
+// The tensor core adds each MMA's products into the fp32 accumulator with TRUNCATION (measured:
+// ~7e-8 relative, biased toward zero, per tcgen05.mma), so one long accumulation chain drifts by
+// ~1e-4 at K = 9216.  Two-level accumulation keeps fp32-class accuracy: the dominant hi*hi
+// products go to a double-buffered TMEM accumulator D1 that the epilogue warps drain into fp32
+// registers (round-to-nearest adds on the CUDA cores) every TC_CHUNK_STAGES pipeline stages; the
+// 2^-11-times-smaller cross terms hi*lo + lo*hi accumulate in their own TMEM tile D2 for the whole
+// K loop (their truncation error is 2^-11 times smaller still).
+constexpr int TC_CHUNK_STAGES = 4;          // 16 hi*hi MMAs per D1 chunk
 
 template <int BN, int STAGES>
 struct TcCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int TMEM_COLS = (3 * BN <= 256) ? 256 : 512;   // D1[0], D1[1], D2
 };
 
 template <int BN, int STAGES>
@@ -226,8 +234,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* acc_full_bar = empty_bar + STAGES;       // [2]
+  uint64_t* acc_empty_bar = acc_full_bar + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x;
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full_bar[s], 1); mbar_init(&acc_empty_bar[s], 4); }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -255,6 +264,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
 
   const int cchunks = a.cin >> 6;
   const int n_iters = a.kh * a.kw * cchunks;
+  const int n_acc_chunks = (n_iters + TC_CHUNK_STAGES - 1) / TC_CHUNK_STAGES;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -280,9 +290,17 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ---------------- MMA issuer: 4 K-slices x {hi*hi, hi*lo, lo*hi}
+      // ---------------- MMA issuer: per K=16 slice  D1 += Ahi*Bhi ;  D2 += Ahi*Blo + Alo*Bhi
       constexpr uint32_t idesc = make_idesc_f16(128, BN);
+      const uint32_t d2 = tmem_base + 2u * BN;
       for (int it = 0; it < n_iters; ++it) {
+        const int chunk = it / TC_CHUNK_STAGES, in_chunk = it % TC_CHUNK_STAGES;
+        const int buf = chunk & 1;
+        if (in_chunk == 0) {                         // D1[buf] must have been drained by the epilogue warps
+          mbar_wait(&acc_empty_bar[buf], (((uint32_t)chunk >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+        }
+        const uint32_t d1 = tmem_base + (uint32_t)buf * BN;
         const int st = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(&full_bar[st], ph);
@@ -295,13 +313,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t ko = (uint64_t)(k * 2);      // 16 fp16 = 32 B = 2 x 16 B units
-          umma_f16(tmem_base, d_ahi + ko, d_bhi + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          umma_f16(tmem_base, d_ahi + ko, d_blo + ko, idesc, 1u);
-          umma_f16(tmem_base, d_alo + ko, d_bhi + ko, idesc, 1u);
+          umma_f16(d1, d_ahi + ko, d_bhi + ko, idesc, (in_chunk > 0 || k > 0) ? 1u : 0u);
+          umma_f16(d2, d_ahi + ko, d_blo + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_f16(d2, d_alo + ko, d_bhi + ko, idesc, 1u);
         }
-        umma_commit(&empty_bar[st]);     // frees the smem slot once these MMAs retire
+        umma_commit(&empty_bar[st]);                  // frees the smem slot once these MMAs retire
+        if (in_chunk == TC_CHUNK_STAGES - 1 || it == n_iters - 1) umma_commit(&acc_full_bar[buf]);
       }
-      umma_commit(tmem_full_bar);        // accumulator complete
     }
   } else {
     // ---------------- epilogue warps 2..5: TMEM lane quadrant = warp % 4
@@ -318,65 +336,100 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     const size_t opix = ((size_t)n_img * a.ho + oy) * a.wo + ox;
     size_t rpix = 0;
     if (a.res_hi) rpix = ((size_t)n_img * a.res_h + (size_t)oy * a.res_stride) * a.res_w + (size_t)ox * a.res_stride;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      const int c0 = n0 + ch * 32;
-      if (c0 >= a.cout) break;                       // warp-uniform
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
-      tmem_ld_wait();
-      if (!valid) continue;
-      float v[32];
-      const bool full = (c0 + 32 <= a.cout);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    // ---- drain D1 chunks into fp32 registers (round-to-nearest adds)
+    float racc[BN];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = c0 + j;
-        const float sc = (full || c < a.cout) ? __ldg(a.scale + c) : 0.f;
-        const float bi = (full || c < a.cout) ? __ldg(a.bias + c) : 0.f;
-        v[j] = fmaf(__uint_as_float(r[j]), sc, bi);
-      }
-      if (a.res_hi) {     // residual tensors always have cout % 32 == 0 channels
-        const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + rpix * a.cout + c0);
-        const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + rpix * a.cout + c0);
+    for (int j = 0; j < BN; ++j) racc[j] = 0.f;
+    for (int c = 0; c < n_acc_chunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&acc_full_bar[buf], ((uint32_t)c >> 1) & 1u);
+      tc_fence_after();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
-          const __half* ph = reinterpret_cast<const __half*>(&h4);
-          const __half* pl = reinterpret_cast<const __half*>(&l4);
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        if (n0 + ch * 32 < a.cout) {                 // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(lane_base + (uint32_t)(buf * BN + ch * 32), r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[g * 8 + j] += join_f16(ph[j], pl[j]);
+          for (int j = 0; j < 32; ++j) racc[ch * 32 + j] = __fadd_rn(racc[ch * 32 + j], __uint_as_float(r[j]));
         }
       }
+      if (c == n_acc_chunks - 1) {                   // the last commit also covers every D2 MMA
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
-      if (a.out_f32) {
-        float* op = a.out_f32 + opix * a.cout + c0;
-        if (full && (a.cout % 4) == 0) {
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          if (n0 + ch * 32 < a.cout) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(lane_base + (uint32_t)(2 * BN + ch * 32), r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            reinterpret_cast<float4*>(op)[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < a.cout) op[j] = v[j];
+            for (int j = 0; j < 32; ++j) racc[ch * 32 + j] = __fadd_rn(racc[ch * 32 + j], __uint_as_float(r[j]));
+          }
         }
-      } else {            // split outputs always have cout % 32 == 0
-        bool ovf = false;
-        uint4 hv[4], lv[4];
-        __half* ph = reinterpret_cast<__half*>(hv);
-        __half* pl = reinterpret_cast<__half*>(lv);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
+    }
+
+    // ---- scale/bias (folded BN) -> +residual -> activation -> store
+    if (valid) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          ovf |= !(fabsf(v[j]) <= LUMI_F16_MAX);
-          split_f32(v[j], ph[j], pl[j]);
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int c0 = n0 + ch * 32;
+        if (c0 < a.cout) {
+          float v[32];
+          const bool full = (c0 + 32 <= a.cout);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = c0 + j;
+            const float sc = (full || c < a.cout) ? __ldg(a.scale + c) : 0.f;
+            const float bi = (full || c < a.cout) ? __ldg(a.bias + c) : 0.f;
+            v[j] = fmaf(racc[ch * 32 + j], sc, bi);
+          }
+          if (a.res_hi) {     // residual tensors always have cout % 32 == 0 channels
+            const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + rpix * a.cout + c0);
+            const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + rpix * a.cout + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
+              const __half* ph = reinterpret_cast<const __half*>(&h4);
+              const __half* pl = reinterpret_cast<const __half*>(&l4);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] += join_f16(ph[j], pl[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
+          if (a.out_f32) {
+            float* op = a.out_f32 + opix * a.cout + c0;
+            if (full && (a.cout % 4) == 0) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                reinterpret_cast<float4*>(op)[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < a.cout) op[j] = v[j];
+            }
+          } else {            // split outputs always have cout % 32 == 0
+            bool ovf = false;
+            uint4 hv[4], lv[4];
+            __half* ph = reinterpret_cast<__half*>(hv);
+            __half* pl = reinterpret_cast<__half*>(lv);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              ovf |= !(fabsf(v[j]) <= LUMI_F16_MAX);
+              split_f32(v[j], ph[j], pl[j]);
+            }
+            uint4* oh = reinterpret_cast<uint4*>(a.out_hi + opix * a.cout + c0);
+            uint4* ol = reinterpret_cast<uint4*>(a.out_lo + opix * a.cout + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) { oh[g] = hv[g]; ol[g] = lv[g]; }
+            if (ovf && a.overflow) atomicOr(a.overflow, 1);
+          }
         }
-        uint4* oh = reinterpret_cast<uint4*>(a.out_hi + opix * a.cout + c0);
-        uint4* ol = reinterpret_cast<uint4*>(a.out_lo + opix * a.cout + c0);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) { oh[g] = hv[g]; ol[g] = lv[g]; }
-        if (ovf && a.overflow) atomicOr(a.overflow, 1);
       }
     }
   }
@@ -511,7 +564,7 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   std::memset(&a, 0, sizeof(a));
   int nb, th, tw;
   pick_tile(io.in.n, io.ho, io.wo, nb, th, tw);
-  const int bn = (L.cout_pad % 256 == 0) ? 256 : (L.cout_pad % 128 == 0 ? 128 : 64);
+  const int bn = (L.cout_pad % 128 == 0) ? 128 : 64;
   a.tm_a_hi = cached_act_map(io.in.hi, io.in.n, io.in.h, io.in.w, io.in.c, nb, th, tw);
   a.tm_a_lo = cached_act_map(io.in.lo, io.in.n, io.in.h, io.in.w, io.in.c, nb, th, tw);
   const int kdim = L.kh * L.kw * L.cin;
@@ -526,8 +579,7 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   a.tiles_w = cdiv(io.wo, tw); a.tiles_h = cdiv(io.ho, th);
   a.overflow = io.overflow_flag;
   dim3 grid((unsigned)(a.tiles_w * a.tiles_h * cdiv(io.in.n, nb)), (unsigned)(L.cout_pad / bn));
-  if (bn == 256) launch_tc_cfg<256, 2>(a, grid, st);
-  else if (bn == 128) launch_tc_cfg<128, 3>(a, grid, st);
+  if (bn == 128) launch_tc_cfg<128, 3>(a, grid, st);
   else launch_tc_cfg<64, 4>(a, grid, st);
 }
 

@@ -110,6 +110,12 @@ struct lumi_engine {
   int* d_prop_counts = nullptr;
   std::map<std::string, Tap> taps;
   int planned_n = 0, planned_h = 0, planned_w = 0;
+  // per-category device timing (CUDA events on the engine stream), for bench.py's roofline
+  bool profile = false;
+  struct ProfSpan { int cat; cudaEvent_t a, b; double work; };
+  std::vector<ProfSpan> prof_spans;
+  std::vector<cudaEvent_t> prof_pool;
+  std::string prof_text;
 
   ~lumi_engine() {
     for (auto& kv : layers) conv_layer_free(kv.second);
@@ -118,6 +124,8 @@ struct lumi_engine {
     cudaFree(d_anchor_ref); cudaFree(d_anchors); cudaFree(d_final_keys); cudaFree(d_ssd_anchors);
     cudaFree(arena.base); cudaFree(d_overflow); cudaFree(d_images);
     cudaFree(d_boxes); cudaFree(d_scores); cudaFree(d_labels); cudaFree(d_counts); cudaFree(d_prop_counts);
+    for (auto& sp : prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto ev : prof_pool) cudaEventDestroy(ev);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -443,6 +451,30 @@ void build_layers(lumi_engine* e) {
   }
 }
 
+// ---------------------------------------------------------------- per-category timing
+enum ProfCat { PC_CONV_TC = 0, PC_CONV_SIMT, PC_POOL, PC_PREP, PC_RPN_POST, PC_ROI, PC_HEAD_MISC, PC_DET_POST, PC_COUNT };
+const char* PROF_NAMES[PC_COUNT] = {"conv_tc", "conv_simt", "pool", "preprocess", "rpn_proposals", "roi_pool",
+                                    "head_misc", "detections"};
+
+cudaEvent_t prof_event(lumi_engine* e) {
+  if (!e->prof_pool.empty()) { cudaEvent_t ev = e->prof_pool.back(); e->prof_pool.pop_back(); return ev; }
+  cudaEvent_t ev;
+  LUMI_CUDA_CHECK(cudaEventCreate(&ev));
+  return ev;
+}
+struct ProfScope {
+  lumi_engine* e; int idx = -1;
+  // work: algorithmic FLOPs (conv) or bytes (HBM-bound stages) of the kernels inside the span
+  ProfScope(lumi_engine* eng, bool dry, int cat, double work = 0.0) : e(eng) {
+    if (dry || !e->profile) return;
+    lumi_engine::ProfSpan sp{cat, prof_event(e), prof_event(e), work};
+    LUMI_CUDA_CHECK(cudaEventRecord(sp.a, e->stream));
+    e->prof_spans.push_back(sp);
+    idx = (int)e->prof_spans.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(e->prof_spans[idx].b, e->stream); }
+};
+
 // ---------------------------------------------------------------- execution context
 struct Ctx {
   lumi_engine* e;
@@ -503,7 +535,10 @@ Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* re
   if (res) { io.res = *res; io.res_stride = res_stride; }
   io.overflow_flag = cx.e->d_overflow;
   if (!cx.dry) {
-    if (cx.e->conv_impl == 1 && conv_tc_supported(L, io)) launch_conv_tc(L, io, cx.st);
+    const bool tc = cx.e->conv_impl == 1 && conv_tc_supported(L, io);
+    const double flops = 2.0 * (double)in.n * ho * wo * (double)L.kh * L.kw * L.cin * L.cout;
+    ProfScope ps(cx.e, cx.dry, tc ? PC_CONV_TC : PC_CONV_SIMT, flops);
+    if (tc) launch_conv_tc(L, io, cx.st);
     else launch_conv_simt(L, io, cx.st);
   }
   return out;
@@ -515,7 +550,7 @@ Act run_pool(Ctx& cx, Act in, int k, int stride, bool same) {
   else { ho = tf_valid(in.h, k, stride, 1); wo = tf_valid(in.w, k, stride, 1); }
   LUMI_REQUIRE(ho > 0 && wo > 0, "max_pool: input too small");
   Act out = cx.act(in.n, ho, wo, in.c);
-  if (!cx.dry) launch_max_pool(in, out, k, stride, pt, pl, cx.st);
+  if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_POOL); launch_max_pool(in, out, k, stride, pt, pl, cx.st); }
   return out;
 }
 
@@ -536,7 +571,7 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   const std::string root = "truncated_base_network/" + e->arch;
   const int* units = e->arch == "resnet_v1_50" ? RESNET_UNITS_50 : RESNET_UNITS_101;
   Act x = cx.act(n, h, w, 3);
-  if (!cx.dry) launch_u8_to_act(images, x, RGB_MEANS, cx.st);          // base_network.py:153-177
+  if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_u8_to_act(images, x, RGB_MEANS, cx.st); }  // base_network.py:153-177
   x = run_conv(cx, root + "/conv1", x, 2, nullptr, 1, nullptr);          // conv2d_same(64, 7, stride 2) + BN + relu
   x = run_pool(cx, x, 3, 2, true);                                       // pool1 3x3/2 SAME
   for (int b = 0; b < 3; ++b)
@@ -573,6 +608,7 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   float* pscores = cx.f32((size_t)n * post);
   if (!cx.dry) {
     LUMI_REQUIRE(na <= e->ws_rpn.cap, "image too large for the RPN workspace (max_h/max_w at lumi_create)");
+    ProfScope ps(cx.e, cx.dry, PC_RPN_POST);
     launch_rpn_proposals(heads, heads, (long)fh * fw * hc, (long)fh * fw * hc, e->A, e->d_anchors, n, rp, e->ws_rpn,
                          proposals, pscores, e->d_prop_counts, cx.st);
   }
@@ -596,8 +632,12 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
 
   // RCNN (rcnn.py:174-232)
   Act pooled = cx.act(n * post, e->pooled_w, e->pooled_h, fmap.c);
-  if (!cx.dry)
+  if (!cx.dry) {
+    // algorithmic bytes: feature map once + rois + pooled output (fp16x2 planes = 4 B / element)
+    const double bytes = 4.0 * fmap.numel() + 16.0 * n * post + 4.0 * (double)pooled.numel();
+    ProfScope ps(cx.e, cx.dry, PC_ROI, bytes);
     launch_roi_pool(fmap, proposals, e->d_prop_counts, post, (float)h, (float)w, e->pooled_h, e->pooled_w, pooled, cx.st);
+  }
   cx.tap_act("roi_pool", pooled);
   Act feat = pooled;
   if (e->arch == "resnet_v1_101" && e->use_tail)                         // truncated_base_network.py:56-95
@@ -605,7 +645,7 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
       feat = bottleneck(cx, root + "/block4/unit_" + std::to_string(u + 1) + "/bottleneck_v1", feat, 2048);
   if (e->use_mean) {
     Act m = cx.act(feat.n, 1, 1, feat.c);
-    if (!cx.dry) launch_spatial_mean(feat, m, cx.st);
+    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_HEAD_MISC); launch_spatial_mean(feat, m, cx.st); }
     feat = m;
   } else {
     feat.c = feat.h * feat.w * feat.c; feat.h = 1; feat.w = 1;           // flatten (NHWC order == tf flatten)
@@ -617,15 +657,17 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   run_conv(cx, "fasterrcnn/rcnn/heads", feat, 1, nullptr, 1, &fc);
   const int C = e->num_classes, fcw = 5 * C + 1;
   float* cls_prob = cx.f32((size_t)n * post * (C + 1));
-  if (!cx.dry) launch_softmax_rows(fc, cls_prob, n * post, C + 1, fcw, cx.st);
+  if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_HEAD_MISC); launch_softmax_rows(fc, cls_prob, n * post, C + 1, fcw, cx.st); }
   cx.tap_f32("rcnn_cls_prob", cls_prob, n, post, C + 1, 1);
   cx.tap_f32("rcnn_fc", fc, n, post, fcw, 1);
   DetParams dp = e->det;
   dp.r = post; dp.im_h = (float)h; dp.im_w = (float)w;
   dp.prob_stride = C + 1; dp.delta_stride = fcw;
-  if (!cx.dry)
+  if (!cx.dry) {
+    ProfScope ps(cx.e, cx.dry, PC_DET_POST);
     launch_class_detections(proposals, (long)post * 4, e->d_prop_counts, fc + (C + 1), cls_prob, n, dp, e->ws_det,
                             e->d_final_keys, e->d_boxes, e->d_labels, e->d_scores, e->d_counts, cx.st);
+  }
 }
 
 // ---------------------------------------------------------------- SSD forward
@@ -700,7 +742,7 @@ void forward_ssd(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   LUMI_REQUIRE(h == e->fixed_h && w == e->fixed_w, "SSD expects images of the configured fixed size");
   const std::string s = "ssd/ssd_feature_extractor";
   Act x = cx.act(n, h, w, 3);
-  if (!cx.dry) launch_u8_to_act(images, x, nullptr, cx.st);             // no mean subtraction (quirk Q7)
+  if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_u8_to_act(images, x, nullptr, cx.st); }  // no mean subtraction (quirk Q7)
   Act fmaps[6];
   for (int b = 0; b < 5; ++b) {
     for (int r = 0; r < VGG_REPS[b]; ++r)
@@ -708,7 +750,7 @@ void forward_ssd(Ctx& cx, const uint8_t* images, int n, int h, int w) {
                    1, nullptr);
     if (b == 3) {                                                         // conv4_3 -> l2norm x gamma
       Act nrm = cx.act(x.n, x.h, x.w, x.c);
-      if (!cx.dry) launch_l2norm_scale(x, nrm, e->dev_vecs.at("gamma"), 1e-12f, cx.st);
+      if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_HEAD_MISC); launch_l2norm_scale(x, nrm, e->dev_vecs.at("gamma"), 1e-12f, cx.st); }
       fmaps[0] = nrm;
     }
     if (b < 4) x = run_pool(cx, x, 2, 2, false);                          // slim default VALID (quirk Q8)
@@ -730,6 +772,7 @@ void forward_ssd(Ctx& cx, const uint8_t* images, int n, int h, int w) {
     Act o = run_conv(cx, "ssd/MultiBox_" + std::to_string(i), fmaps[i], 1, nullptr, 1, &head);
     const int A = e->ssd_app[i], cells = o.h * o.w, per_cell = A * (4 + C1);
     if (!cx.dry) {
+      ProfScope ps(cx.e, cx.dry, PC_HEAD_MISC);
       dim3 g(cdiv(cells * per_cell, 256), n);
       ssd_repack_kernel<<<g, 256, 0, cx.st>>>(head, cells, A, C1, total, off, loc, cls);
       count_launch();
@@ -739,15 +782,17 @@ void forward_ssd(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   }
   LUMI_REQUIRE(off == total, "SSD anchor count mismatch (internal)");
   float* prob = cx.f32((size_t)n * total * C1);
-  if (!cx.dry) launch_softmax_rows(cls, prob, n * total, C1, C1, cx.st);
+  if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_HEAD_MISC); launch_softmax_rows(cls, prob, n * total, C1, C1, cx.st); }
   cx.tap_f32("loc_pred", loc, n, total, 4, 1);
   cx.tap_f32("cls_prob", prob, n, total, C1, 1);
   cx.tap_f32("all_anchors", e->d_ssd_anchors, total, 4, 1, 1);
   DetParams dp = e->det;
   dp.r = total; dp.im_h = (float)h; dp.im_w = (float)w; dp.prob_stride = C1; dp.delta_stride = 4;
-  if (!cx.dry)
+  if (!cx.dry) {
+    ProfScope ps(cx.e, cx.dry, PC_DET_POST);
     launch_class_detections(e->d_ssd_anchors, 0, nullptr, loc, prob, n, dp, e->ws_det, e->d_final_keys, e->d_boxes,
                             e->d_labels, e->d_scores, e->d_counts, cx.st);
+  }
 }
 
 void forward(Ctx& cx, const uint8_t* images, int n, int h, int w) {
@@ -971,6 +1016,35 @@ int lumi_set_conv_impl(lumi_engine* e, int impl) {
   if (!e || (impl != 0 && impl != 1)) return LUMI_EINVAL;
   e->conv_impl = impl;
   return LUMI_OK;
+}
+
+int lumi_profile_enable(lumi_engine* e, int enable) {
+  if (!e) return LUMI_EINVAL;
+  e->profile = enable != 0;
+  return LUMI_OK;
+}
+
+// Drains the recorded spans: "name:spans:total_ms:work;..." accumulated since the last read
+// (work = algorithmic FLOPs for conv categories, algorithmic bytes for roi_pool, 0 otherwise).
+const char* lumi_profile_read(lumi_engine* e) {
+  if (!e) return "";
+  try {
+    cudaSetDevice(e->device);
+    LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    double ms[PC_COUNT] = {0}, work[PC_COUNT] = {0};
+    int cnt[PC_COUNT] = {0};
+    for (auto& sp : e->prof_spans) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) { ms[sp.cat] += t; cnt[sp.cat]++; work[sp.cat] += sp.work; }
+      e->prof_pool.push_back(sp.a); e->prof_pool.push_back(sp.b);
+    }
+    e->prof_spans.clear();
+    e->prof_text.clear();
+    for (int c = 0; c < PC_COUNT; ++c)
+      e->prof_text += std::string(PROF_NAMES[c]) + ":" + std::to_string(cnt[c]) + ":" + std::to_string(ms[c]) + ":" +
+                      std::to_string(work[c]) + ";";
+  } catch (const Error& err) { e->last_error = err.what(); return ""; }
+  return e->prof_text.c_str();
 }
 
 int lumi_get_tensor(lumi_engine* e, const char* name, float* out, int64_t capacity, int64_t* numel, int64_t* shape4) {

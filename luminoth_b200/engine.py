@@ -43,6 +43,8 @@ SIGNATURES = {
     'lumi_synchronize': (ctypes.c_int, [ctypes.c_void_p]),
     'lumi_last_launch_count': (ctypes.c_int, [ctypes.c_void_p]),
     'lumi_set_conv_impl': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    'lumi_profile_enable': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    'lumi_profile_read': (ctypes.c_char_p, [ctypes.c_void_p]),
     'lumi_get_tensor': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, _c_i64_p,
                                        _c_i64_p]),
     'lumi_last_error': (ctypes.c_char_p, [ctypes.c_void_p]),
@@ -209,6 +211,20 @@ class Engine(object):
                                         ctypes.c_void_p(labels.data_ptr()), ctypes.c_void_p(counts.data_ptr()), 1)
             if rc != LUMI_OK:
                 _raise(rc, self._lib.lumi_last_error(self._h))
+
+    def profile(self, enable=True):
+        self._lib.lumi_profile_enable(self._h, int(bool(enable)))
+
+    def profile_read(self):
+        """{category: (spans, total_ms, work)} accumulated since the last read
+        (work = algorithmic FLOPs for conv_*, algorithmic bytes for roi_pool)."""
+        txt = self._lib.lumi_profile_read(self._h).decode()
+        out = {}
+        for part in txt.split(';'):
+            if part:
+                name, cnt, ms, work = part.split(':')
+                out[name] = (int(cnt), float(ms), float(work))
+        return out
 
     def synchronize(self):
         rc = self._lib.lumi_synchronize(self._h)

@@ -132,7 +132,7 @@ def ssd_weights(config, seed=0, profile='peaky'):
         wts[n + '_offsets_conv/w'] = _conv(rng, 3, 3, ch, 4 * A, std=0.1 / np.sqrt(fan))
         wts[n + '_offsets_conv/b'] = np.zeros(4 * A, np.float32)
         wts[n + '_classes_conv/w'] = _conv(rng, 3, 3, ch, (C + 1) * A,
-                                           std=(3.0 if peaky else 1.0) / np.sqrt(fan))
+                                           std=(0.7 if peaky else 0.25) / np.sqrt(fan))
         wts[n + '_classes_conv/b'] = np.zeros((C + 1) * A, np.float32)
     return wts
 

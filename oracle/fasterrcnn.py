@@ -109,11 +109,12 @@ def rcnn_head(pooled, wts, rcfg, arch, scope='fasterrcnn/rcnn', use_tail=True):
             feats = feats.reshape(0, feats.shape[-1])
     net = feats.reshape(feats.shape[0], -1)
     act = {'relu6': T.relu6, 'relu': T.relu}[rcfg.get('activation_function', 'relu6')]
+    dt = net.dtype
     for i, _ in enumerate(rcfg.get('layer_sizes') or []):
-        net = act(net @ wts['%s/fc_%d/w' % (scope, i)] + wts['%s/fc_%d/b' % (scope, i)])
-    cls_score = net @ wts[scope + '/fc_classifier/w'] + wts[scope + '/fc_classifier/b']
+        net = act(net @ wts['%s/fc_%d/w' % (scope, i)].astype(dt) + wts['%s/fc_%d/b' % (scope, i)].astype(dt))
+    cls_score = net @ wts[scope + '/fc_classifier/w'].astype(dt) + wts[scope + '/fc_classifier/b'].astype(dt)
     cls_prob = T.softmax(cls_score)
-    bbox_offsets = net @ wts[scope + '/fc_bbox/w'] + wts[scope + '/fc_bbox/b']
+    bbox_offsets = net @ wts[scope + '/fc_bbox/w'].astype(dt) + wts[scope + '/fc_bbox/b'].astype(dt)
     return {'features': net, 'cls_score': cls_score, 'cls_prob': cls_prob,
             'bbox_offsets': bbox_offsets}
 
@@ -153,12 +154,14 @@ def rcnn_proposal(proposals, bbox_pred, cls_prob, im_shape, num_classes, pcfg,
 
 
 # ---------------------------------------------------------------- full model
-def forward(image, wts, config):
+def forward(image, wts, config, dtype=np.float32):
     """``FasterRCNN._build`` (``fasterrcnn.py:70-156``), inference.
-    image: (H,W,3) float32 (already resized); returns prediction dict."""
+    image: (H,W,3) (already resized); returns prediction dict.  dtype=float64
+    runs the conv / FC arithmetic in double (tests use it as the exact-arithmetic
+    yardstick for fp32 noise); box post-processing always runs in fp32 like TF."""
     m = config['model']
     arch = m['base_network']['architecture']
-    image = np.asarray(image, np.float32)
+    image = np.asarray(image, dtype)
     fmap = resnet.trunk(image[None], wts, arch,
                         output_stride=m['base_network'].get('output_stride', 16))
     im_shape = image.shape[:2]

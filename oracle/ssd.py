@@ -59,12 +59,12 @@ def ssd_proposal(cls_prob, loc_pred, all_anchors, im_shape, num_classes, pcfg, v
     return {'objects': proposals[idx].reshape(-1, 4), 'labels': labels[idx], 'probs': top_probs}
 
 
-def forward(image, wts, config):
-    """``SSD._build`` inference; image (300,300,3) float32 raw 0..255."""
+def forward(image, wts, config, dtype=np.float32):
+    """``SSD._build`` inference; image (300,300,3) raw 0..255 (dtype=float64: see fasterrcnn.forward)."""
     m = config['model']
     ip = config['dataset']['image_preprocessing']
     image_shape = [ip['fixed_height'], ip['fixed_width'], 3]     # ssd.py:30-31,63
-    image = np.asarray(image, np.float32)
+    image = np.asarray(image, dtype)
     assert list(image.shape) == image_shape, image.shape
     fmaps = ssd_feature_maps(image[None], wts)
     nc = m['network']['num_classes']

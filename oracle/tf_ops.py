@@ -42,6 +42,9 @@ def conv2d(x, w, stride=1, padding='SAME', rate=1, bias=None):
     ``ssd.py:83-96``; ``feature_extractor.py:28-37``.
     """
     kh, kw = w.shape[0], w.shape[1]
+    w = w.astype(x.dtype, copy=False)
+    if bias is not None:
+        bias = bias.astype(x.dtype, copy=False)
     xt = _t(x).permute(0, 3, 1, 2)
     wt = _t(w).permute(3, 2, 0, 1).contiguous()
     if padding == 'SAME':

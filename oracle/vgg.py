@@ -30,7 +30,7 @@ def ssd_feature_maps(images, wts, scope='ssd/ssd_feature_extractor'):
             x = T.max_pool(x, 2, 2, 'VALID')
     fmaps = OrderedDict()
     norm = T.l2_normalize(conv4_3, 3, 1e-12)
-    fmaps['conv4_3_norm'] = (norm * wts[scope + '/conv_4_3_norm/gamma'].reshape(1, 1, 1, -1)
+    fmaps['conv4_3_norm'] = (norm * wts[scope + '/conv_4_3_norm/gamma'].reshape(1, 1, 1, -1).astype(images.dtype)
                              ).astype(images.dtype)
     e = scope + '/extra_feature_layers'
 
