@@ -83,6 +83,10 @@ const char* lumi_profile_read(lumi_engine* e);
  * 1 = tcgen05 fp16x2-split tensor-core kernel wherever the layer qualifies (default). */
 int lumi_set_conv_impl(lumi_engine* e, int impl);
 
+/* 1: also materialise intermediates the fused production path never writes (the "roi_pool" tap when
+ * ROI crop + max-pool + mean run as one kernel) -- config.train.debug in the reference. Default 0. */
+int lumi_set_debug_taps(lumi_engine* e, int enable);
+
 /* Debug taps for parity tests (models' debug fetches, predicting.py:104-107):
  * copy a named intermediate of the LAST lumi_predict to host as fp32.
  * Names: "conv_feature_map", "rpn_cls_prob", "rpn_bbox_pred", "all_anchors",

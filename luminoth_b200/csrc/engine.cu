@@ -72,6 +72,7 @@ struct lumi_engine {
   bool finalized = false;
   int conv_impl = 1;
   int launches = 0;
+  bool debug_taps = false;      // materialise intermediates that the fused path skips (roi_pool)
 
   std::string type, arch;
   int num_classes = 0;
@@ -631,24 +632,33 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   }
 
   // RCNN (rcnn.py:174-232)
-  Act pooled = cx.act(n * post, e->pooled_w, e->pooled_h, fmap.c);
+  const bool has_tail = e->arch == "resnet_v1_101" && e->use_tail;      // truncated_base_network.py:56-95
+  const bool fuse_mean = e->use_mean && !has_tail;                        // ROI crop+max-pool+mean in one kernel
+  const bool need_pooled = !fuse_mean || e->debug_taps;
+  Act pooled, feat;
+  if (need_pooled) pooled = cx.act(n * post, e->pooled_w, e->pooled_h, fmap.c);
+  if (fuse_mean) feat = cx.act(n * post, 1, 1, fmap.c);
   if (!cx.dry) {
-    // algorithmic bytes: feature map once + rois + pooled output (fp16x2 planes = 4 B / element)
-    const double bytes = 4.0 * fmap.numel() + 16.0 * n * post + 4.0 * (double)pooled.numel();
+    // algorithmic bytes: feature map once + rois + output (fp16x2 planes = 4 B / element)
+    const double bytes = 4.0 * fmap.numel() + 16.0 * n * post + 4.0 * (double)(need_pooled ? pooled.numel() : 0) +
+                         4.0 * (double)(fuse_mean ? feat.numel() : 0);
     ProfScope ps(cx.e, cx.dry, PC_ROI, bytes);
-    launch_roi_pool(fmap, proposals, e->d_prop_counts, post, (float)h, (float)w, e->pooled_h, e->pooled_w, pooled, cx.st);
+    launch_roi_pool(fmap, proposals, e->d_prop_counts, post, (float)h, (float)w, e->pooled_h, e->pooled_w, pooled,
+                    fuse_mean ? feat : Act(), cx.st);
   }
-  cx.tap_act("roi_pool", pooled);
-  Act feat = pooled;
-  if (e->arch == "resnet_v1_101" && e->use_tail)                         // truncated_base_network.py:56-95
-    for (int u = 0; u < 3; ++u)
-      feat = bottleneck(cx, root + "/block4/unit_" + std::to_string(u + 1) + "/bottleneck_v1", feat, 2048);
-  if (e->use_mean) {
-    Act m = cx.act(feat.n, 1, 1, feat.c);
-    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_HEAD_MISC); launch_spatial_mean(feat, m, cx.st); }
-    feat = m;
-  } else {
-    feat.c = feat.h * feat.w * feat.c; feat.h = 1; feat.w = 1;           // flatten (NHWC order == tf flatten)
+  if (need_pooled) cx.tap_act("roi_pool", pooled);
+  if (!fuse_mean) {
+    feat = pooled;
+    if (has_tail)
+      for (int u = 0; u < 3; ++u)
+        feat = bottleneck(cx, root + "/block4/unit_" + std::to_string(u + 1) + "/bottleneck_v1", feat, 2048);
+    if (e->use_mean) {
+      Act m = cx.act(feat.n, 1, 1, feat.c);
+      if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_HEAD_MISC); launch_spatial_mean(feat, m, cx.st); }
+      feat = m;
+    } else {
+      feat.c = feat.h * feat.w * feat.c; feat.h = 1; feat.w = 1;         // flatten (NHWC order == tf flatten)
+    }
   }
   cx.tap_act("rcnn_features", feat);
   for (size_t i = 0; i < e->fc_sizes.size(); ++i)
@@ -1011,6 +1021,13 @@ int lumi_synchronize(lumi_engine* e) {
 }
 
 int lumi_last_launch_count(lumi_engine* e) { return e ? e->launches : 0; }
+
+int lumi_set_debug_taps(lumi_engine* e, int enable) {
+  if (!e) return LUMI_EINVAL;
+  e->debug_taps = enable != 0;
+  e->planned_n = 0;          // the plan (arena layout) changes
+  return LUMI_OK;
+}
 
 int lumi_set_conv_impl(lumi_engine* e, int impl) {
   if (!e || (impl != 0 && impl != 1)) return LUMI_EINVAL;

@@ -15,9 +15,10 @@ void launch_softmax_rows(const float* x, float* y, int rows, int cols, int in_st
 void launch_frcnn_anchors(const int* ref /*A x 4*/, int A, int fh, int fw, int stride, float* out, cudaStream_t st);
 
 // ---- ROI crop + 2x2 max pool (roi.cu) : roi_pool.py:68-95
-// rois [nimg][rmax][4] (x1,y1,x2,y2 px), counts [nimg] (nullptr -> all rmax valid); out (nimg*rmax, ph, pw, C)
+// rois [nimg][rmax][4] (x1,y1,x2,y2 px), counts [nimg] (nullptr -> all rmax valid); out (nimg*rmax, pw, ph, C)
+// and/or mean (nimg*rmax, 1, 1, C) = tf.reduce_mean over the pooled cells (either may be an empty Act).
 void launch_roi_pool(Act fmap, const float* rois, const int* counts, int rmax, float im_h, float im_w, int ph, int pw,
-                     Act out, cudaStream_t st);
+                     Act out, Act mean, cudaStream_t st);
 
 // ---- proposal / detection chains (postproc.cu)
 struct NmsWorkspace {

@@ -42,18 +42,27 @@ __device__ __forceinline__ float4 clip_box(float4 b, float im_h, float im_w) {
 __device__ __forceinline__ bool area_positive(float4 b) {
   return __fmul_rn(fmaxf(__fsub_rn(b.z, b.x), 0.f), fmaxf(__fsub_rn(b.w, b.y), 0.f)) > 0.f;
 }
-// tf.image.non_max_suppression's IoU test on (x1,y1,x2,y2) boxes.
+// tf.image.non_max_suppression's IoU test on (x1,y1,x2,y2) boxes:  iou(a, b) > thr  with
+//   iou = inter / (area_a + area_b - inter)  in fp32, 0 when either area <= 0.
+// Bit-identical to evaluating the division, but the IEEE divide only runs for the rare pairs whose
+// ratio is within 2^-20 of the threshold (non-overlapping pairs -- the vast majority -- exit first).
 __device__ __forceinline__ bool iou_gt(float4 a, float4 b, float thr) {
   const float ymin_i = fminf(a.y, a.w), xmin_i = fminf(a.x, a.z), ymax_i = fmaxf(a.y, a.w), xmax_i = fmaxf(a.x, a.z);
   const float ymin_j = fminf(b.y, b.w), xmin_j = fminf(b.x, b.z), ymax_j = fmaxf(b.y, b.w), xmax_j = fmaxf(b.x, b.z);
   const float area_i = __fmul_rn(__fsub_rn(ymax_i, ymin_i), __fsub_rn(xmax_i, xmin_i));
   const float area_j = __fmul_rn(__fsub_rn(ymax_j, ymin_j), __fsub_rn(xmax_j, xmin_j));
-  if (area_i <= 0.f || area_j <= 0.f) return false;
+  if (area_i <= 0.f || area_j <= 0.f) return 0.f > thr;
   const float iy0 = fmaxf(ymin_i, ymin_j), ix0 = fmaxf(xmin_i, xmin_j);
   const float iy1 = fminf(ymax_i, ymax_j), ix1 = fminf(xmax_i, xmax_j);
   const float inter = __fmul_rn(fmaxf(__fsub_rn(iy1, iy0), 0.f), fmaxf(__fsub_rn(ix1, ix0), 0.f));
-  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
-  return iou > thr;
+  const float uni = __fsub_rn(__fadd_rn(area_i, area_j), inter);
+  if (inter == 0.f && uni > 0.f) return 0.f > thr;              // 0 / positive == +0 exactly
+  if (thr > 0.f && uni > 1e-30f && uni < 1e30f && inter < 1e30f) {
+    const float t = __fmul_rn(thr, uni);
+    if (inter < __fmul_rn(t, 0.99999905f)) return false;        // ratio < thr (1 - 2^-20): RN(ratio) <= thr
+    if (inter > __fmul_rn(t, 1.00000095f)) return true;         // ratio > thr (1 + 2^-20): RN(ratio) >  thr
+  }
+  return __fdiv_rn(inter, uni) > thr;
 }
 
 // ------------------------------------------------------------------ workspace
@@ -245,12 +254,15 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   }
 }
 
-// serial-scan reduce: one CTA per problem walks 64-box chunks in score order.
+// serial-scan reduce: one CTA per problem walks 64-box chunks in score order.  Per chunk: thread 0
+// resolves the 64x64 diagonal word greedily (find-first-set over the still-alive bits, so the loop runs
+// once per KEPT box), then all threads OR the kept rows into the running "removed" words.  The next
+// chunk's diagonal words do not depend on the removal state, so they are prefetched during the OR phase.
 __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long* __restrict__ mask,
                                                        const int* __restrict__ nvalid, int cap, int words,
                                                        int max_out, int* __restrict__ keep, int* __restrict__ nkeep) {
   extern __shared__ unsigned long long removed[];     // [words]
-  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long diag[2][64];
   __shared__ int s_kept[64];
   __shared__ int s_nk, s_total, s_done;
   const int p = blockIdx.x;
@@ -259,36 +271,49 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long*
   const unsigned long long* M = mask + (size_t)p * cap * words;
   for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = 0ull;
   if (threadIdx.x == 0) { s_total = 0; s_done = (max_out <= 0 || n == 0) ? 1 : 0; }
+  if (threadIdx.x < 64) diag[0][threadIdx.x] = (int)threadIdx.x < n ? M[(size_t)threadIdx.x * words] : 0ull;
   __syncthreads();
-  for (int c = 0; c < nw && !s_done; ++c) {
-    if (threadIdx.x < 64) {
-      const int row = c * 64 + threadIdx.x;
-      diag[threadIdx.x] = row < n ? M[(size_t)row * words + c] : 0ull;
-    }
-    __syncthreads();
+  const bool done0 = s_done != 0;                      // read by everyone before thread 0 can change it
+  for (int c = 0; c < nw && !done0; ++c) {
+    const unsigned long long* dg = diag[c & 1];
     if (threadIdx.x == 0) {
       unsigned long long cur = removed[c];
-      int nk = 0, total = s_total;
       const int lim = min(64, n - c * 64);
-      for (int b = 0; b < lim; ++b) {
-        if (!((cur >> b) & 1ull)) {
-          s_kept[nk++] = b;
-          keep[(size_t)p * max_out + total] = c * 64 + b;
-          ++total;
-          if (total >= max_out) { s_done = 1; break; }
-          cur |= diag[b];
-        }
+      const unsigned long long vmask = lim == 64 ? ~0ull : ((1ull << lim) - 1ull);
+      unsigned long long avail = ~cur & vmask;
+      int nk = 0, total = s_total;
+      while (avail) {
+        const int b = __ffsll((long long)avail) - 1;
+        s_kept[nk++] = b;
+        keep[(size_t)p * max_out + total] = c * 64 + b;
+        if (++total >= max_out) { s_done = 1; break; }
+        cur |= dg[b];
+        avail = ~cur & vmask & ~((2ull << b) - 1ull);      // alive bits above b
       }
       s_nk = nk; s_total = total;
     }
     __syncthreads();
     if (s_done) break;
+    unsigned long long next_diag = 0ull;               // prefetch (independent of the removal state)
+    if (threadIdx.x < 64) {
+      const int row = (c + 1) * 64 + threadIdx.x;
+      if (row < n) next_diag = M[(size_t)row * words + (c + 1)];
+    }
     const int nk = s_nk;
     for (int w = c + 1 + threadIdx.x; w < nw; w += blockDim.x) {
       unsigned long long acc = removed[w];
-      for (int i = 0; i < nk; ++i) acc |= M[(size_t)(c * 64 + s_kept[i]) * words + w];
+      int i = 0;
+      for (; i + 4 <= nk; i += 4) {
+        const unsigned long long a0 = M[(size_t)(c * 64 + s_kept[i]) * words + w];
+        const unsigned long long a1 = M[(size_t)(c * 64 + s_kept[i + 1]) * words + w];
+        const unsigned long long a2 = M[(size_t)(c * 64 + s_kept[i + 2]) * words + w];
+        const unsigned long long a3 = M[(size_t)(c * 64 + s_kept[i + 3]) * words + w];
+        acc |= (a0 | a1) | (a2 | a3);
+      }
+      for (; i < nk; ++i) acc |= M[(size_t)(c * 64 + s_kept[i]) * words + w];
       removed[w] = acc;
     }
+    if (threadIdx.x < 64) diag[(c + 1) & 1][threadIdx.x] = next_diag;
     __syncthreads();
   }
   if (threadIdx.x == 0) nkeep[p] = s_total;

@@ -15,7 +15,8 @@ struct RoiArgs {
   const float* rois; const int* counts; int rmax;
   float im_h, im_w;
   int crop_h, crop_w;        // 2*pw, 2*ph  (sic)
-  __half* ohi; __half* olo;  // (n*rmax, crop_h/2, crop_w/2, c)
+  __half* ohi; __half* olo;  // (n*rmax, crop_h/2, crop_w/2, c) or nullptr (mean only)
+  __half* mhi; __half* mlo;  // optional fused tf.reduce_mean over the pooled cells: (n*rmax, c)
 };
 
 __device__ __forceinline__ void load8(const __half* hi, const __half* lo, size_t off, float (&v)[8]) {
@@ -46,6 +47,9 @@ __global__ void __launch_bounds__(256) roi_pool_kernel(const RoiArgs a) {
   const __half* fhi = a.fhi + (size_t)img * a.fh * a.fw * a.c;
   const __half* flo = a.flo + (size_t)img * a.fh * a.fw * a.c;
 
+  float msum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) msum[j] = 0.f;
   for (int cell = warp; cell < oh * ow; cell += 8) {
     if (c0 >= a.c) break;
     const int py = cell / ow, px = cell % ow;
@@ -88,25 +92,48 @@ __global__ void __launch_bounds__(256) roi_pool_kernel(const RoiArgs a) {
         }
       }
     }
-    uint4 vh, vl;
-    __half* qh = reinterpret_cast<__half*>(&vh);
-    __half* ql = reinterpret_cast<__half*>(&vl);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) split_f32(best[j], qh[j], ql[j]);
-    const size_t off = obase + (size_t)cell * a.c + c0;
-    *reinterpret_cast<uint4*>(a.ohi + off) = vh;
-    *reinterpret_cast<uint4*>(a.olo + off) = vl;
+    for (int j = 0; j < 8; ++j) msum[j] += best[j];
+    if (a.ohi) {
+      uint4 vh, vl;
+      __half* qh = reinterpret_cast<__half*>(&vh);
+      __half* ql = reinterpret_cast<__half*>(&vl);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_f32(best[j], qh[j], ql[j]);
+      const size_t off = obase + (size_t)cell * a.c + c0;
+      *reinterpret_cast<uint4*>(a.ohi + off) = vh;
+      *reinterpret_cast<uint4*>(a.olo + off) = vl;
+    }
+  }
+  if (a.mhi) {            // fused spatial mean (rcnn.py:188): warp partials -> fixed-order sum -> / cells
+    __shared__ float part[8][256];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[warp][lane * 8 + j] = msum[j];
+    __syncthreads();
+    const int ch = cslice + threadIdx.x;
+    if (ch < a.c) {
+      float s = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) s += part[w8][threadIdx.x];
+      const float v = __fdiv_rn(s, (float)(oh * ow));
+      __half h, l;
+      split_f32(v, h, l);
+      a.mhi[(size_t)row * a.c + ch] = h;
+      a.mlo[(size_t)row * a.c + ch] = l;
+    }
   }
 }
 
 void launch_roi_pool(Act fmap, const float* rois, const int* counts, int rmax, float im_h, float im_w, int ph, int pw,
-                     Act out, cudaStream_t st) {
+                     Act out, Act mean, cudaStream_t st) {
   LUMI_REQUIRE(fmap.c % 8 == 0, "roi_pool: C must be a multiple of 8");
   RoiArgs a;
   a.fhi = fmap.hi; a.flo = fmap.lo; a.n = fmap.n; a.fh = fmap.h; a.fw = fmap.w; a.c = fmap.c;
   a.rois = rois; a.counts = counts; a.rmax = rmax; a.im_h = im_h; a.im_w = im_w;
   a.crop_h = pw * 2; a.crop_w = ph * 2;      // roi_pool.py:77 passes [pooled_width*2, pooled_height*2]
   a.ohi = out.hi; a.olo = out.lo;
+  a.mhi = mean.hi; a.mlo = mean.lo;
+  LUMI_REQUIRE(out.hi || mean.hi, "roi_pool: no output requested");
   long rows = (long)fmap.n * rmax;
   if (!rows) return;
   dim3 grid((unsigned)rows, (unsigned)cdiv(fmap.c, 256));

@@ -71,7 +71,11 @@ def test_fasterrcnn_stages_and_detections(arch, impl):
     eng = Engine(cfg, max_batch=2, max_h=h, max_w=w)
     eng.load_weights(wts).finalize()
     eng.set_conv_impl(impl)
+    fused = eng.predict_raw(imgs)                      # production path (ROI crop+pool+mean fused for R50)
+    eng.set_debug_taps(True)                           # also materialise the roi_pool tap
     boxes, scores, labels, counts = eng.predict_raw(imgs)
+    for a, b in zip(fused, (boxes, scores, labels, counts)):
+        np.testing.assert_array_equal(a, b)            # taps must not change the result
     fmap = eng.get_tensor('conv_feature_map')
     heads = eng.get_tensor('rpn_heads')
     props = eng.get_tensor('proposals')
