@@ -205,7 +205,9 @@ struct TcArgs {
   int n, ho, wo, cin, cout;
   int kh, kw, rate, pad_t, pad_l, act;
   int nb, th, tw;                  // M tile = nb images x th rows x tw cols (<= 128 pixels)
-  int tiles_w, tiles_h;
+  int tiles_w, tiles_h, tiles_n;   // M tiles per row / column / image groups
+  int n_tiles;                     // C_out tiles (cout_pad / BN)
+  int stride;                      // TMA traversal stride of the activation map (1 or 2)
   int* overflow;
 };
 
@@ -224,32 +226,38 @@ struct TcCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = (3 * BN <= 256) ? 256 : 512;   // D1[0], D1[1], D2
+  static constexpr int TMEM_COLS = 4 * BN;          // D1[0], D1[1], D2[0], D2[1]  (256 or 512 columns)
 };
 
+constexpr int TC_THREADS = 320;                     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
+// Persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, += gridDim.x.  The
+// TMA producer, the MMA issuer and the epilogue warps each iterate the same tile sequence with
+// free-running stage / chunk counters, so the producer prefetches the next tile's operands and the
+// tensor core starts the next tile while the epilogue warps are still storing the previous one
+// (D1 and D2 are double-buffered in TMEM).
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   using Cfg = TcCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_full_bar = empty_bar + STAGES;       // [2]
-  uint64_t* acc_empty_bar = acc_full_bar + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
+  uint64_t* acc_full_bar = empty_bar + STAGES;       // [2]  D1[buf] chunk complete (tcgen05.commit)
+  uint64_t* acc_empty_bar = acc_full_bar + 2;        // [2]  D1[buf] drained by the 8 epilogue warps
+  uint64_t* d2_empty_bar = acc_empty_bar + 2;        // [2]  D2[tbuf] drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x;
-  const int tile_x = mt % a.tiles_w;
-  const int tile_y = (mt / a.tiles_w) % a.tiles_h;
-  const int tile_n = mt / (a.tiles_w * a.tiles_h);
-  const int x0 = tile_x * a.tw, y0 = tile_y * a.th, img0 = tile_n * a.nb;
-  const int n0 = blockIdx.y * BN;
+  const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
+  const int total_tiles = m_tiles * a.n_tiles;
   const int rows_valid = a.nb * a.th * a.tw;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full_bar[s], 1); mbar_init(&acc_empty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full_bar[s], 1); mbar_init(&acc_empty_bar[s], 8); mbar_init(&d2_empty_bar[s], 8);
+    }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -270,21 +278,25 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     if (lane == 0) {
       // ---------------- TMA producer: one (tap, 64-channel) slice per stage
       const uint32_t stage_tx = 2u * (uint32_t)rows_valid * 128u + 2u * (uint32_t)Cfg::B_BYTES;
-      int it = 0;
-      for (int tap = 0; tap < a.kh * a.kw; ++tap) {
-        const int r = tap / a.kw, s = tap % a.kw;
-        const int iy = y0 + r * a.rate - a.pad_t, ix = x0 + s * a.rate - a.pad_l;
-        for (int cc = 0; cc < cchunks; ++cc, ++it) {
-          const int st = it % STAGES;
-          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-          mbar_wait(&empty_bar[st], ph ^ 1u);
-          uint8_t* sbase = smem + st * Cfg::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[st], stage_tx);
-          tma_load_4d(sbase, &a.tm_a_hi, &full_bar[st], cc * 64, ix, iy, img0);
-          tma_load_4d(sbase + TC_A_BYTES, &a.tm_a_lo, &full_bar[st], cc * 64, ix, iy, img0);
-          const int kcol = tap * a.cin + cc * 64;
-          tma_load_2d(sbase + 2 * TC_A_BYTES, &a.tm_b_hi, &full_bar[st], kcol, n0);
-          tma_load_2d(sbase + 2 * TC_A_BYTES + Cfg::B_BYTES, &a.tm_b_lo, &full_bar[st], kcol, n0);
+      uint32_t git = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+        const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
+        const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
+        for (int tap = 0; tap < a.kh * a.kw; ++tap) {
+          const int r = tap / a.kw, s = tap % a.kw;
+          const int iy = y0 * a.stride + r * a.rate - a.pad_t, ix = x0 * a.stride + s * a.rate - a.pad_l;
+          for (int cc = 0; cc < cchunks; ++cc, ++git) {
+            const uint32_t st = git % STAGES, ph = (git / STAGES) & 1u;
+            mbar_wait(&empty_bar[st], ph ^ 1u);
+            uint8_t* sbase = smem + st * Cfg::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[st], stage_tx);
+            tma_load_4d(sbase, &a.tm_a_hi, &full_bar[st], cc * 64, ix, iy, img0);
+            tma_load_4d(sbase + TC_A_BYTES, &a.tm_a_lo, &full_bar[st], cc * 64, ix, iy, img0);
+            const int kcol = tap * a.cin + cc * 64;
+            tma_load_2d(sbase + 2 * TC_A_BYTES, &a.tm_b_hi, &full_bar[st], kcol, n0);
+            tma_load_2d(sbase + 2 * TC_A_BYTES + Cfg::B_BYTES, &a.tm_b_lo, &full_bar[st], kcol, n0);
+          }
         }
       }
     }
@@ -292,142 +304,168 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     if (lane == 0) {
       // ---------------- MMA issuer: per K=16 slice  D1 += Ahi*Bhi ;  D2 += Ahi*Blo + Alo*Bhi
       constexpr uint32_t idesc = make_idesc_f16(128, BN);
-      const uint32_t d2 = tmem_base + 2u * BN;
-      for (int it = 0; it < n_iters; ++it) {
-        const int chunk = it / TC_CHUNK_STAGES, in_chunk = it % TC_CHUNK_STAGES;
-        const int buf = chunk & 1;
-        if (in_chunk == 0) {                         // D1[buf] must have been drained by the epilogue warps
-          mbar_wait(&acc_empty_bar[buf], (((uint32_t)chunk >> 1) & 1u) ^ 1u);
-          tc_fence_after();
-        }
-        const uint32_t d1 = tmem_base + (uint32_t)buf * BN;
-        const int st = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&full_bar[st], ph);
+      uint32_t git = 0, gchunk = 0, tile_iter = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+        const uint32_t tbuf = tile_iter & 1u;
+        mbar_wait(&d2_empty_bar[tbuf], ((tile_iter >> 1) & 1u) ^ 1u);     // previous user of D2[tbuf] drained
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
-        const uint64_t d_ahi = make_sw128_kmajor_desc(sa);
-        const uint64_t d_alo = make_sw128_kmajor_desc(sa + TC_A_BYTES);
-        const uint64_t d_bhi = make_sw128_kmajor_desc(sa + 2 * TC_A_BYTES);
-        const uint64_t d_blo = make_sw128_kmajor_desc(sa + 2 * TC_A_BYTES + Cfg::B_BYTES);
+        const uint32_t d2 = tmem_base + (2u + tbuf) * BN;
+        uint32_t d1 = 0, buf = 0;
+        for (int it = 0; it < n_iters; ++it, ++git) {
+          const int in_chunk = it % TC_CHUNK_STAGES;
+          if (in_chunk == 0) {
+            buf = gchunk & 1u;
+            mbar_wait(&acc_empty_bar[buf], ((gchunk >> 1) & 1u) ^ 1u);    // D1[buf] drained
+            tc_fence_after();
+            d1 = tmem_base + buf * BN;
+          }
+          const uint32_t st = git % STAGES, ph = (git / STAGES) & 1u;
+          mbar_wait(&full_bar[st], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
+          const uint64_t d_ahi = make_sw128_kmajor_desc(sa);
+          const uint64_t d_alo = make_sw128_kmajor_desc(sa + TC_A_BYTES);
+          const uint64_t d_bhi = make_sw128_kmajor_desc(sa + 2 * TC_A_BYTES);
+          const uint64_t d_blo = make_sw128_kmajor_desc(sa + 2 * TC_A_BYTES + Cfg::B_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ko = (uint64_t)(k * 2);      // 16 fp16 = 32 B = 2 x 16 B units
-          umma_f16(d1, d_ahi + ko, d_bhi + ko, idesc, (in_chunk > 0 || k > 0) ? 1u : 0u);
-          umma_f16(d2, d_ahi + ko, d_blo + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          umma_f16(d2, d_alo + ko, d_bhi + ko, idesc, 1u);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2);      // 16 fp16 = 32 B = 2 x 16 B units
+            umma_f16(d1, d_ahi + ko, d_bhi + ko, idesc, (in_chunk > 0 || k > 0) ? 1u : 0u);
+            umma_f16(d2, d_ahi + ko, d_blo + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_f16(d2, d_alo + ko, d_bhi + ko, idesc, 1u);
+          }
+          umma_commit(&empty_bar[st]);                  // frees the smem slot once these MMAs retire
+          if (in_chunk == TC_CHUNK_STAGES - 1 || it == n_iters - 1) {
+            umma_commit(&acc_full_bar[buf]);            // D1[buf] (and, on the last chunk, D2[tbuf]) complete
+            ++gchunk;
+          }
         }
-        umma_commit(&empty_bar[st]);                  // frees the smem slot once these MMAs retire
-        if (in_chunk == TC_CHUNK_STAGES - 1 || it == n_iters - 1) umma_commit(&acc_full_bar[buf]);
       }
     }
   } else {
-    // ---------------- epilogue warps 2..5: TMEM lane quadrant = warp % 4
+    // ---------------- epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp-2)/4
+    constexpr int HC = BN / 2;                          // columns owned by this warp
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    bool valid = row < rows_valid;
-    int n_img = 0, oy = 0, ox = 0;
-    if (valid) {
-      int nl = row / (a.th * a.tw);
-      int rem = row % (a.th * a.tw);
-      n_img = img0 + nl; oy = y0 + rem / a.tw; ox = x0 + rem % a.tw;
-      valid = n_img < a.n && oy < a.ho && ox < a.wo;
-    }
-    const size_t opix = ((size_t)n_img * a.ho + oy) * a.wo + ox;
-    size_t rpix = 0;
-    if (a.res_hi) rpix = ((size_t)n_img * a.res_h + (size_t)oy * a.res_stride) * a.res_w + (size_t)ox * a.res_stride;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-
-    // ---- drain D1 chunks into fp32 registers (round-to-nearest adds)
-    float racc[BN];
-#pragma unroll
-    for (int j = 0; j < BN; ++j) racc[j] = 0.f;
-    for (int c = 0; c < n_acc_chunks; ++c) {
-      const int buf = c & 1;
-      mbar_wait(&acc_full_bar[buf], ((uint32_t)c >> 1) & 1u);
-      tc_fence_after();
-#pragma unroll
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        if (n0 + ch * 32 < a.cout) {                 // warp-uniform
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(lane_base + (uint32_t)(buf * BN + ch * 32), r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) racc[ch * 32 + j] = __fadd_rn(racc[ch * 32 + j], __uint_as_float(r[j]));
-        }
+    uint32_t gchunk = 0, tile_iter = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+      const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+      const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
+      const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb;
+      const int n0 = nt * BN + half * HC;               // first channel of this warp's columns
+      const uint32_t tbuf = tile_iter & 1u;
+      bool valid = row < rows_valid;
+      int n_img = 0, oy = 0, ox = 0;
+      if (valid) {
+        const int nl = row / (a.th * a.tw);
+        const int rem = row % (a.th * a.tw);
+        n_img = img0 + nl; oy = y0 + rem / a.tw; ox = x0 + rem % a.tw;
+        valid = n_img < a.n && oy < a.ho && ox < a.wo;
       }
-      if (c == n_acc_chunks - 1) {                   // the last commit also covers every D2 MMA
+      const size_t opix = ((size_t)n_img * a.ho + oy) * a.wo + ox;
+      size_t rpix = 0;
+      if (a.res_hi)
+        rpix = ((size_t)n_img * a.res_h + (size_t)oy * a.res_stride) * a.res_w + (size_t)ox * a.res_stride;
+
+      // ---- drain D1 chunks into fp32 registers (round-to-nearest adds)
+      float racc[HC];
 #pragma unroll
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          if (n0 + ch * 32 < a.cout) {
+      for (int j = 0; j < HC; ++j) racc[j] = 0.f;
+      for (int c = 0; c < n_acc_chunks; ++c, ++gchunk) {
+        const uint32_t buf = gchunk & 1u;
+        mbar_wait(&acc_full_bar[buf], (gchunk >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < HC / 32; ++ch) {
+          if (n0 + ch * 32 < a.cout) {                   // warp-uniform
             uint32_t r[32];
-            tmem_ld_32x32b_x32(lane_base + (uint32_t)(2 * BN + ch * 32), r);
+            tmem_ld_32x32b_x32(lane_base + (uint32_t)(buf * BN + half * HC + ch * 32), r);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) racc[ch * 32 + j] = __fadd_rn(racc[ch * 32 + j], __uint_as_float(r[j]));
           }
         }
+        if (c == n_acc_chunks - 1) {                     // the last commit also covers every D2 MMA of the tile
+#pragma unroll
+          for (int ch = 0; ch < HC / 32; ++ch) {
+            if (n0 + ch * 32 < a.cout) {
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(lane_base + (uint32_t)((2 + tbuf) * BN + half * HC + ch * 32), r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) racc[ch * 32 + j] = __fadd_rn(racc[ch * 32 + j], __uint_as_float(r[j]));
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&d2_empty_bar[tbuf]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
-    }
 
-    // ---- scale/bias (folded BN) -> +residual -> activation -> store
-    if (valid) {
+      // ---- scale/bias (folded BN) -> +residual -> activation -> store (overlaps the next tile's MMAs)
+      if (valid) {
 #pragma unroll
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        const int c0 = n0 + ch * 32;
-        if (c0 < a.cout) {
-          float v[32];
-          const bool full = (c0 + 32 <= a.cout);
+        for (int ch = 0; ch < HC / 32; ++ch) {
+          const int c0 = n0 + ch * 32;
+          if (c0 < a.cout) {
+            float v[32];
+            const bool full = (c0 + 32 <= a.cout);
+            // scale / bias vectors are padded to cout_pad: 16 B loads are always in bounds
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            const float sc = (full || c < a.cout) ? __ldg(a.scale + c) : 0.f;
-            const float bi = (full || c < a.cout) ? __ldg(a.bias + c) : 0.f;
-            v[j] = fmaf(racc[ch * 32 + j], sc, bi);
-          }
-          if (a.res_hi) {     // residual tensors always have cout % 32 == 0 channels
-            const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + rpix * a.cout + c0);
-            const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + rpix * a.cout + c0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
-              const __half* ph = reinterpret_cast<const __half*>(&h4);
-              const __half* pl = reinterpret_cast<const __half*>(&l4);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[g * 8 + j] += join_f16(ph[j], pl[j]);
+            for (int g = 0; g < 8; ++g) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + c0) + g);
+              const float4 bi = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + g);
+              v[g * 4 + 0] = fmaf(racc[ch * 32 + g * 4 + 0], sc.x, bi.x);
+              v[g * 4 + 1] = fmaf(racc[ch * 32 + g * 4 + 1], sc.y, bi.y);
+              v[g * 4 + 2] = fmaf(racc[ch * 32 + g * 4 + 2], sc.z, bi.z);
+              v[g * 4 + 3] = fmaf(racc[ch * 32 + g * 4 + 3], sc.w, bi.w);
             }
-          }
+            if (a.res_hi) {     // residual tensors always have cout % 32 == 0 channels
+              const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + rpix * a.cout + c0);
+              const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + rpix * a.cout + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
-          if (a.out_f32) {
-            float* op = a.out_f32 + opix * a.cout + c0;
-            if (full && (a.cout % 4) == 0) {
+              for (int g = 0; g < 4; ++g) {
+                uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
+                const __half* ph = reinterpret_cast<const __half*>(&h4);
+                const __half* pl = reinterpret_cast<const __half*>(&l4);
 #pragma unroll
-              for (int g = 0; g < 8; ++g)
-                reinterpret_cast<float4*>(op)[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + j < a.cout) op[j] = v[j];
+                for (int j = 0; j < 8; ++j) v[g * 8 + j] += join_f16(ph[j], pl[j]);
+              }
             }
-          } else {            // split outputs always have cout % 32 == 0
-            bool ovf = false;
-            uint4 hv[4], lv[4];
-            __half* ph = reinterpret_cast<__half*>(hv);
-            __half* pl = reinterpret_cast<__half*>(lv);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              ovf |= !(fabsf(v[j]) <= LUMI_F16_MAX);
-              split_f32(v[j], ph[j], pl[j]);
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
+            if (a.out_f32) {
+              float* op = a.out_f32 + opix * a.cout + c0;
+              if (full && (a.cout % 4) == 0) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                  reinterpret_cast<float4*>(op)[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (c0 + j < a.cout) op[j] = v[j];
+              }
+            } else {            // split outputs always have cout % 32 == 0
+              bool ovf = false;
+              uint4 hv[4], lv[4];
+              __half* ph = reinterpret_cast<__half*>(hv);
+              __half* pl = reinterpret_cast<__half*>(lv);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                ovf |= !(fabsf(v[j]) <= LUMI_F16_MAX);
+                split_f32(v[j], ph[j], pl[j]);
+              }
+              uint4* oh = reinterpret_cast<uint4*>(a.out_hi + opix * a.cout + c0);
+              uint4* ol = reinterpret_cast<uint4*>(a.out_lo + opix * a.cout + c0);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) { oh[g] = hv[g]; ol[g] = lv[g]; }
+              if (ovf && a.overflow) atomicOr(a.overflow, 1);
             }
-            uint4* oh = reinterpret_cast<uint4*>(a.out_hi + opix * a.cout + c0);
-            uint4* ol = reinterpret_cast<uint4*>(a.out_lo + opix * a.cout + c0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) { oh[g] = hv[g]; ol[g] = lv[g]; }
-            if (ovf && a.overflow) atomicOr(a.overflow, 1);
           }
         }
       }
@@ -459,12 +497,18 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static CUtensorMap make_map_act(const __half* base, int n, int h, int w, int c, int nb, int th, int tw) {
+// `stride` > 1 (strided conv): TMA traversal stride along W and H -- the box spans tw*stride x th*stride
+// input pixels and every stride-th one is copied, so smem still receives tw x th rows.
+static CUtensorMap make_map_act(const __half* base, int n, int h, int w, int c, int nb, int th, int tw, int stride,
+                                long pix_pitch, long row_pitch, long img_pitch) {
   CUtensorMap m;
+  if (!pix_pitch) pix_pitch = c;
+  if (!row_pitch) row_pitch = (long)w * c;
+  if (!img_pitch) img_pitch = (long)h * w * c;
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)pix_pitch * 2, (cuuint64_t)row_pitch * 2, (cuuint64_t)img_pitch * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), (cuuint32_t)nb};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -495,13 +539,14 @@ struct MapKey {
 static std::map<MapKey, CUtensorMap> g_map_cache;
 static std::mutex g_map_mutex;
 
-static CUtensorMap cached_act_map(const __half* base, int n, int h, int w, int c, int nb, int th, int tw) {
+static CUtensorMap cached_act_map(const __half* base, int n, int h, int w, int c, int nb, int th, int tw, int stride,
+                                  long pix_pitch, long row_pitch, long img_pitch) {
   std::lock_guard<std::mutex> lk(g_map_mutex);
-  MapKey k{base, n, h, w, c, nb, th, tw};
+  MapKey k{base, n, h, w, c + (int)(pix_pitch << 12), nb, th * 16 + stride, tw};
   auto it = g_map_cache.find(k);
   if (it != g_map_cache.end()) return it->second;
   if (g_map_cache.size() > 4096) g_map_cache.clear();
-  CUtensorMap m = make_map_act(base, n, h, w, c, nb, th, tw);
+  CUtensorMap m = make_map_act(base, n, h, w, c, nb, th, tw, stride, pix_pitch, row_pitch, img_pitch);
   g_map_cache[k] = m;
   return m;
 }
@@ -535,15 +580,26 @@ static void pick_tile(int n, int ho, int wo, int& nb, int& th, int& tw) {
 
 bool conv_tc_supported(const ConvLayer& L, const ConvIO& io) {
   if (!L.tc_ready) return false;
-  if (L.stride != 1) return false;
+  if (L.stride != 1 && L.stride != 2) return false;
+  if (L.stride == 2 && L.rate != 1) return false;
   if (L.cin % 64 != 0) return false;
   if (io.out_f32 == nullptr && (L.cout % 32) != 0) return false;
   if (io.res.hi && (L.cout % 32) != 0) return false;
   return true;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    LUMI_CUDA_CHECK(cudaGetDevice(&dev));
+    LUMI_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
 template <int BN, int STAGES>
-static void launch_tc_cfg(const TcArgs& a, dim3 grid, cudaStream_t st) {
+static void launch_tc_cfg(const TcArgs& a, cudaStream_t st) {
   using Cfg = TcCfg<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -551,7 +607,9 @@ static void launch_tc_cfg(const TcArgs& a, dim3 grid, cudaStream_t st) {
                                          Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  conv_tc_kernel<BN, STAGES><<<grid, 192, Cfg::SMEM_BYTES, st>>>(a);
+  const long total = (long)a.tiles_w * a.tiles_h * a.tiles_n * a.n_tiles;
+  const int grid = (int)(total < sm_count() ? total : sm_count());     // persistent: one CTA per SM
+  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
@@ -565,8 +623,10 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   int nb, th, tw;
   pick_tile(io.in.n, io.ho, io.wo, nb, th, tw);
   const int bn = (L.cout_pad % 128 == 0) ? 128 : 64;
-  a.tm_a_hi = cached_act_map(io.in.hi, io.in.n, io.in.h, io.in.w, io.in.c, nb, th, tw);
-  a.tm_a_lo = cached_act_map(io.in.lo, io.in.n, io.in.h, io.in.w, io.in.c, nb, th, tw);
+  a.tm_a_hi = cached_act_map(io.in.hi, io.in.n, io.in.h, io.in.w, io.in.c, nb, th, tw, L.stride, io.in_pix_pitch,
+                             io.in_row_pitch, io.in_img_pitch);
+  a.tm_a_lo = cached_act_map(io.in.lo, io.in.n, io.in.h, io.in.w, io.in.c, nb, th, tw, L.stride, io.in_pix_pitch,
+                             io.in_row_pitch, io.in_img_pitch);
   const int kdim = L.kh * L.kw * L.cin;
   a.tm_b_hi = cached_wgt_map(L.w_hi, L.cout_pad, kdim, bn);
   a.tm_b_lo = cached_wgt_map(L.w_lo, L.cout_pad, kdim, bn);
@@ -576,11 +636,12 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   a.n = io.in.n; a.ho = io.ho; a.wo = io.wo; a.cin = L.cin; a.cout = L.cout;
   a.kh = L.kh; a.kw = L.kw; a.rate = L.rate; a.pad_t = io.pad_t; a.pad_l = io.pad_l; a.act = L.act;
   a.nb = nb; a.th = th; a.tw = tw;
-  a.tiles_w = cdiv(io.wo, tw); a.tiles_h = cdiv(io.ho, th);
+  a.tiles_w = cdiv(io.wo, tw); a.tiles_h = cdiv(io.ho, th); a.tiles_n = cdiv(io.in.n, nb);
+  a.n_tiles = L.cout_pad / bn;
+  a.stride = L.stride;
   a.overflow = io.overflow_flag;
-  dim3 grid((unsigned)(a.tiles_w * a.tiles_h * cdiv(io.in.n, nb)), (unsigned)(L.cout_pad / bn));
-  if (bn == 128) launch_tc_cfg<128, 3>(a, grid, st);
-  else launch_tc_cfg<64, 4>(a, grid, st);
+  if (bn == 128) launch_tc_cfg<128, 3>(a, st);
+  else launch_tc_cfg<64, 4>(a, st);
 }
 
 // ---------------------------------------------------------------- host: weight packing
@@ -589,15 +650,16 @@ void conv_layer_upload(ConvLayer& L, const float* w, const float* scale, const f
   const size_t nw = kdim * L.cout;
   LUMI_CUDA_CHECK(cudaMalloc(&L.w_f32, nw * sizeof(float)));
   LUMI_CUDA_CHECK(cudaMemcpy(L.w_f32, w, nw * sizeof(float), cudaMemcpyHostToDevice));
-  std::vector<float> sc(L.cout, 1.f), bi(L.cout, 0.f);
+  const int cpad = cdiv(L.cout, 128) * 128;        // vectors padded so the tcgen05 epilogue can use 16 B loads
+  std::vector<float> sc(cpad, 1.f), bi(cpad, 0.f);
   if (scale) std::memcpy(sc.data(), scale, L.cout * sizeof(float));
   if (bias) std::memcpy(bi.data(), bias, L.cout * sizeof(float));
-  LUMI_CUDA_CHECK(cudaMalloc(&L.scale, L.cout * sizeof(float)));
-  LUMI_CUDA_CHECK(cudaMalloc(&L.bias, L.cout * sizeof(float)));
-  LUMI_CUDA_CHECK(cudaMemcpy(L.scale, sc.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice));
-  LUMI_CUDA_CHECK(cudaMemcpy(L.bias, bi.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice));
+  LUMI_CUDA_CHECK(cudaMalloc(&L.scale, cpad * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMalloc(&L.bias, cpad * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMemcpy(L.scale, sc.data(), cpad * sizeof(float), cudaMemcpyHostToDevice));
+  LUMI_CUDA_CHECK(cudaMemcpy(L.bias, bi.data(), cpad * sizeof(float), cudaMemcpyHostToDevice));
   L.tc_ready = false;
-  if (L.cin % 64 == 0 && L.stride == 1) {
+  if (L.cin % 64 == 0 && (L.stride == 1 || L.stride == 2)) {
     // [cout_pad][kdim] fp16 hi/lo of w * 2^e[c]; e[c] puts max|w[:,c]| in [2^13, 2^14)
     L.cout_pad = cdiv(L.cout, 64) * 64;
     if (L.cout_pad > 64 && L.cout_pad % 128 != 0) L.cout_pad = cdiv(L.cout, 128) * 128;

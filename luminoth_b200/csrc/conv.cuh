@@ -31,6 +31,10 @@ struct ConvIO {
   int pad_t = 0, pad_l = 0;
   int ho = 0, wo = 0;
   int* overflow_flag = nullptr;
+  // Optional strided ("Toeplitz") view of the input for the tcgen05 path: element pitches between
+  // consecutive pixels / rows / images (0 = dense NHWC).  Used by the space-to-depth stem, where each
+  // A row is the 64 contiguous fp16 of four horizontally adjacent 16-channel pixels.
+  long in_pix_pitch = 0, in_row_pitch = 0, in_img_pitch = 0;
 };
 
 // host-side packing (w: TF layout on host)

@@ -25,6 +25,45 @@ void launch_u8_to_act(const uint8_t* img, Act out, const float* means, cudaStrea
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
 
+// Space-to-depth staging of the 7x7/2 stem (slim conv2d_same: zero pad 3/3 AFTER mean subtraction):
+// X2[n][Y][X][dy*6 + dx*3 + c] = xp[2Y+dy][2X+dx][c], xp = padded (image - mean); channels 12..15 = 0.
+// The stem then is a 4x4/1 VALID conv over X2 that the tcgen05 kernel runs as 4 taps of K = 64.
+__global__ void stem_s2d_kernel(const uint8_t* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo, int n,
+                                int h, int w, int h2, int w2, float m0, float m1, float m2) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)n * h2 * w2;
+  if (i >= total) return;
+  const int X = (int)(i % w2), Y = (int)((i / w2) % h2), ni = (int)(i / ((size_t)w2 * h2));
+  uint4 vh[2], vl[2];
+  __half* ph = reinterpret_cast<__half*>(vh);
+  __half* pl = reinterpret_cast<__half*>(vl);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { ph[j] = __float2half_rn(0.f); pl[j] = __float2half_rn(0.f); }
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int py = 2 * Y + dy - 3, px = 2 * X + dx - 3;
+      if (py >= 0 && py < h && px >= 0 && px < w) {
+        const uint8_t* p = img + (((size_t)ni * h + py) * w + px) * 3;
+        const float v0 = __fsub_rn((float)p[0], m0), v1 = __fsub_rn((float)p[1], m1), v2 = __fsub_rn((float)p[2], m2);
+        const int o = dy * 6 + dx * 3;
+        split_f32(v0, ph[o], pl[o]); split_f32(v1, ph[o + 1], pl[o + 1]); split_f32(v2, ph[o + 2], pl[o + 2]);
+      }
+    }
+  uint4* oh = reinterpret_cast<uint4*>(hi + i * 16);
+  uint4* ol = reinterpret_cast<uint4*>(lo + i * 16);
+  oh[0] = vh[0]; oh[1] = vh[1]; ol[0] = vl[0]; ol[1] = vl[1];
+}
+void launch_stem_s2d(const uint8_t* img, int n, int h, int w, Act x2, const float* means, cudaStream_t st) {
+  size_t total = (size_t)n * x2.h * x2.w;
+  if (!total) return;
+  stem_s2d_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(img, x2.hi, x2.lo, n, h, w, x2.h, x2.w, means[0],
+                                                                means[1], means[2]);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
 __global__ void f32_to_act_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
                                   size_t numel) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -393,6 +393,29 @@ void build_layers(lumi_engine* e) {
     const std::string root = "truncated_base_network/" + e->arch;
     const int* units = e->arch == "resnet_v1_50" ? RESNET_UNITS_50 : RESNET_UNITS_101;
     make_conv_bn(e, root + "/conv1", 2, 1, ACT_RELU);
+    {   // tcgen05 form of the stem: 7x7/2 over 3 channels == 4x4/1 over the 12(+4 pad)-channel
+        // space-to-depth input; one filter row r' = 4 taps x 16 ch = one K=64 slice  (kh=4, kw=1, cin=64)
+      const HostTensor& w = W(e, root + "/conv1/weights");
+      const ConvLayer& base = e->layers.at(root + "/conv1");
+      std::vector<float> w2((size_t)4 * 64 * 64, 0.f);
+      for (int rp = 0; rp < 4; ++rp)
+        for (int sp = 0; sp < 4; ++sp)
+          for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+              const int r = 2 * rp + dy, sx = 2 * sp + dx;
+              if (r >= 7 || sx >= 7) continue;
+              for (int c = 0; c < 3; ++c)
+                for (int co = 0; co < 64; ++co)
+                  w2[((size_t)rp * 64 + sp * 16 + dy * 6 + dx * 3 + c) * 64 + co] = w.v[(((size_t)r * 7 + sx) * 3 + c) * 64 + co];
+            }
+      std::vector<float> sc(64), bi(64);
+      LUMI_CUDA_CHECK(cudaMemcpy(sc.data(), base.scale, 64 * sizeof(float), cudaMemcpyDeviceToHost));
+      LUMI_CUDA_CHECK(cudaMemcpy(bi.data(), base.bias, 64 * sizeof(float), cudaMemcpyDeviceToHost));
+      ConvLayer L;
+      L.kh = 4; L.kw = 1; L.cin = 64; L.cout = 64; L.stride = 1; L.rate = 1; L.act = ACT_RELU;
+      conv_layer_upload(L, w2.data(), sc.data(), bi.data());
+      e->layers[root + "/conv1#s2d"] = L;
+    }
     int cin = 64;
     const bool tail = e->arch == "resnet_v1_101" && e->use_tail && e->with_rcnn;
     const int nblocks = tail ? 4 : 3;
@@ -504,7 +527,8 @@ struct Ctx {
 };
 
 // padding: 0 VALID, 1 SAME, 2 slim conv2d_same (explicit pad + VALID when stride > 1)
-Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* res, int res_stride, float** out_f32) {
+Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* res, int res_stride, float** out_f32,
+             const long* view_pitch = nullptr, double algorithmic_flops = -1.0) {
   auto it = cx.e->layers.find(key);
   if (it == cx.e->layers.end()) throw Error(LUMI_ESTATE, "layer '" + key + "' missing (internal)");
   const ConvLayer& L = it->second;
@@ -534,10 +558,13 @@ Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* re
     io.out = out;
   }
   if (res) { io.res = *res; io.res_stride = res_stride; }
+  if (view_pitch) { io.in_pix_pitch = view_pitch[0]; io.in_row_pitch = view_pitch[1]; io.in_img_pitch = view_pitch[2]; }
   io.overflow_flag = cx.e->d_overflow;
   if (!cx.dry) {
     const bool tc = cx.e->conv_impl == 1 && conv_tc_supported(L, io);
-    const double flops = 2.0 * (double)in.n * ho * wo * (double)L.kh * L.kw * L.cin * L.cout;
+    const double flops = algorithmic_flops >= 0 ? algorithmic_flops
+                                                : 2.0 * (double)in.n * ho * wo * (double)L.kh * L.kw * L.cin * L.cout;
+    LUMI_REQUIRE(tc || !view_pitch, "strided input views exist only on the tcgen05 path (internal)");
     ProfScope ps(cx.e, cx.dry, tc ? PC_CONV_TC : PC_CONV_SIMT, flops);
     if (tc) launch_conv_tc(L, io, cx.st);
     else launch_conv_simt(L, io, cx.st);
@@ -571,9 +598,21 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   lumi_engine* e = cx.e;
   const std::string root = "truncated_base_network/" + e->arch;
   const int* units = e->arch == "resnet_v1_50" ? RESNET_UNITS_50 : RESNET_UNITS_101;
-  Act x = cx.act(n, h, w, 3);
-  if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_u8_to_act(images, x, RGB_MEANS, cx.st); }  // base_network.py:153-177
-  x = run_conv(cx, root + "/conv1", x, 2, nullptr, 1, nullptr);          // conv2d_same(64, 7, stride 2) + BN + relu
+  Act x;
+  if (e->conv_impl == 1) {
+    // stem on the tensor cores: mean-subtract + zero-pad + space-to-depth staging, then 4 taps of K=64
+    const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
+    Act x2 = cx.act(n, ho + 3, wo + 3, 16);
+    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_stem_s2d(images, n, h, w, x2, RGB_MEANS, cx.st); }
+    Act view = x2;                      // Toeplitz view: pixel (y, x) -> the 64 contiguous fp16 starting at x2[y][x]
+    view.w = wo; view.c = 64;
+    const long pitch[3] = {16, (long)(wo + 3) * 16, (long)(ho + 3) * (wo + 3) * 16};
+    x = run_conv(cx, root + "/conv1#s2d", view, 0, nullptr, 1, nullptr, pitch, 2.0 * n * ho * wo * 147.0 * 64.0);
+  } else {
+    x = cx.act(n, h, w, 3);
+    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_u8_to_act(images, x, RGB_MEANS, cx.st); }  // base_network.py:153-177
+    x = run_conv(cx, root + "/conv1", x, 2, nullptr, 1, nullptr);        // conv2d_same(64, 7, stride 2) + BN + relu
+  }
   x = run_pool(cx, x, 3, 2, true);                                       // pool1 3x3/2 SAME
   for (int b = 0; b < 3; ++b)
     for (int u = 0; u < units[b]; ++u)
@@ -1032,6 +1071,7 @@ int lumi_set_debug_taps(lumi_engine* e, int enable) {
 int lumi_set_conv_impl(lumi_engine* e, int impl) {
   if (!e || (impl != 0 && impl != 1)) return LUMI_EINVAL;
   e->conv_impl = impl;
+  e->planned_n = 0;          // the plan differs (stem staging buffers)
   return LUMI_OK;
 }
 

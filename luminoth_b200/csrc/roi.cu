@@ -28,7 +28,44 @@ __device__ __forceinline__ void load8(const __half* hi, const __half* lo, size_t
   for (int j = 0; j < 8; ++j) v[j] = join_f16(ph[j], pl[j]);
 }
 
-__global__ void __launch_bounds__(256) roi_pool_kernel(const RoiArgs a) {
+// horizontal lerp of one feature row at the two x samples of a pooled cell; column loads are shared
+// between the two samples whenever they hit the same feature cell (all indices are warp-uniform).
+__device__ __forceinline__ void row_interp(const __half* fhi, const __half* flo, size_t rowbase, int c, int c0,
+                                           const int (&lef)[2], const int (&rig)[2], const float (&xl)[2],
+                                           float (&h0)[8], float (&h1)[8]) {
+  float l0[8], r0[8], l1[8], r1[8];
+  load8(fhi, flo, (rowbase + lef[0]) * c + c0, l0);
+  if (rig[0] != lef[0]) load8(fhi, flo, (rowbase + rig[0]) * c + c0, r0);
+  else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r0[j] = l0[j];
+  }
+  if (lef[1] == lef[0]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l1[j] = l0[j];
+  } else if (lef[1] == rig[0]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l1[j] = r0[j];
+  } else {
+    load8(fhi, flo, (rowbase + lef[1]) * c + c0, l1);
+  }
+  if (rig[1] == rig[0]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r1[j] = r0[j];
+  } else if (rig[1] == lef[1]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r1[j] = l1[j];
+  } else {
+    load8(fhi, flo, (rowbase + rig[1]) * c + c0, r1);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    h0[j] = __fadd_rn(l0[j], __fmul_rn(__fsub_rn(r0[j], l0[j]), xl[0]));
+    h1[j] = __fadd_rn(l1[j], __fmul_rn(__fsub_rn(r1[j], l1[j]), xl[1]));
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) roi_pool_kernel(const RoiArgs a) {
   const int row = blockIdx.x;                 // global roi row = img*rmax + r
   const int img = row / a.rmax, r = row % a.rmax;
   const int cslice = blockIdx.y * 256;
@@ -57,38 +94,69 @@ __global__ void __launch_bounds__(256) roi_pool_kernel(const RoiArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) best[j] = live ? -INFINITY : 0.f;
     if (live) {
+      // sample coordinates of the 2x2 crop samples under this pooled cell (TF crop_and_resize arithmetic)
+      int top[2], bot[2], lef[2], rig[2];
+      float yl[2], xl[2];
+      bool y_ok[2], x_ok[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float in_y = a.crop_h > 1 ? __fadd_rn(__fmul_rn(y1, Hm1), __fmul_rn((float)(py * 2 + s), hs))
+                                        : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(y1, y2)), Hm1);
+        y_ok[s] = !(in_y < 0.f || in_y > Hm1);
+        top[s] = y_ok[s] ? (int)floorf(in_y) : 0;
+        bot[s] = y_ok[s] ? (int)ceilf(in_y) : 0;
+        yl[s] = __fsub_rn(in_y, (float)top[s]);
+        const float in_x = a.crop_w > 1 ? __fadd_rn(__fmul_rn(x1, Wm1), __fmul_rn((float)(px * 2 + s), ws))
+                                        : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(x1, x2)), Wm1);
+        x_ok[s] = !(in_x < 0.f || in_x > Wm1);
+        lef[s] = x_ok[s] ? (int)floorf(in_x) : 0;
+        rig[s] = x_ok[s] ? (int)ceilf(in_x) : 0;
+        xl[s] = __fsub_rn(in_x, (float)lef[s]);
+      }
+      // row-interpolated values, shared between the two y samples when they touch the same feature rows
+      float ht[2][8], hb[2][8];          // [sx][ch] for the current sy: top row / bottom row
+      float pt[2][8], pb[2][8];          // previous sy (sy = 0)
 #pragma unroll
       for (int sy = 0; sy < 2; ++sy) {
-        const int cy = py * 2 + sy;
-        const float in_y = a.crop_h > 1 ? __fadd_rn(__fmul_rn(y1, Hm1), __fmul_rn((float)cy, hs))
-                                        : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(y1, y2)), Hm1);
-        const bool y_ok = !(in_y < 0.f || in_y > Hm1);
-        const int top = (int)floorf(in_y), bot = (int)ceilf(in_y);
-        const float yl = __fsub_rn(in_y, (float)top);
+        if (sy == 0) {
+          row_interp(fhi, flo, (size_t)top[0] * a.fw, a.c, c0, lef, rig, xl, ht[0], ht[1]);
+          if (bot[0] != top[0]) row_interp(fhi, flo, (size_t)bot[0] * a.fw, a.c, c0, lef, rig, xl, hb[0], hb[1]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { hb[0][j] = ht[0][j]; hb[1][j] = ht[1][j]; }
+          }
+        } else {
+          if (top[1] == top[0]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ht[0][j] = pt[0][j]; ht[1][j] = pt[1][j]; }
+          } else if (top[1] == bot[0]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ht[0][j] = pb[0][j]; ht[1][j] = pb[1][j]; }
+          } else {
+            row_interp(fhi, flo, (size_t)top[1] * a.fw, a.c, c0, lef, rig, xl, ht[0], ht[1]);
+          }
+          if (bot[1] == bot[0]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { hb[0][j] = pb[0][j]; hb[1][j] = pb[1][j]; }
+          } else if (bot[1] == top[1]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { hb[0][j] = ht[0][j]; hb[1][j] = ht[1][j]; }
+          } else {
+            row_interp(fhi, flo, (size_t)bot[1] * a.fw, a.c, c0, lef, rig, xl, hb[0], hb[1]);
+          }
+        }
 #pragma unroll
         for (int sx = 0; sx < 2; ++sx) {
-          const int cx = px * 2 + sx;
-          const float in_x = a.crop_w > 1 ? __fadd_rn(__fmul_rn(x1, Wm1), __fmul_rn((float)cx, ws))
-                                          : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(x1, x2)), Wm1);
-          const bool ok = y_ok && !(in_x < 0.f || in_x > Wm1);
-          if (!ok) {              // extrapolation_value = 0
-#pragma unroll
-            for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], 0.f);
-            continue;
-          }
-          const int lef = (int)floorf(in_x), rig = (int)ceilf(in_x);
-          const float xl = __fsub_rn(in_x, (float)lef);
-          float tl[8], tr[8], bl[8], br[8];
-          load8(fhi, flo, ((size_t)top * a.fw + lef) * a.c + c0, tl);
-          load8(fhi, flo, ((size_t)top * a.fw + rig) * a.c + c0, tr);
-          load8(fhi, flo, ((size_t)bot * a.fw + lef) * a.c + c0, bl);
-          load8(fhi, flo, ((size_t)bot * a.fw + rig) * a.c + c0, br);
+          const bool ok = y_ok[sy] && x_ok[sx];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float tv = __fadd_rn(tl[j], __fmul_rn(__fsub_rn(tr[j], tl[j]), xl));
-            const float bv = __fadd_rn(bl[j], __fmul_rn(__fsub_rn(br[j], bl[j]), xl));
-            best[j] = fmaxf(best[j], __fadd_rn(tv, __fmul_rn(__fsub_rn(bv, tv), yl)));
+            const float v = ok ? __fadd_rn(ht[sx][j], __fmul_rn(__fsub_rn(hb[sx][j], ht[sx][j]), yl[sy])) : 0.f;
+            best[j] = fmaxf(best[j], v);              // extrapolation_value = 0
           }
+        }
+        if (sy == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { pt[0][j] = ht[0][j]; pt[1][j] = ht[1][j]; pb[0][j] = hb[0][j]; pb[1][j] = hb[1][j]; }
         }
       }
     }

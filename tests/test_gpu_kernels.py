@@ -72,7 +72,7 @@ CONV_CASES = [
 @pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv2d_matches_oracle(case, impl):
     name, n, h, w, cin, cout, k, stride, rate, padding, use_res, act = case
-    if impl == 'tc' and (stride != 1 or cin % 64 != 0):
+    if impl == 'tc' and cin % 64 != 0:
         pytest.skip('layer shape runs on the SIMT kernel by design')
     import zlib
     rng = np.random.default_rng(zlib.crc32(name.encode()))
