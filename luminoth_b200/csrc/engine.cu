@@ -965,16 +965,14 @@ int lumi_finalize(lumi_engine* e) {
     nms_workspace_alloc(e->ws_rpn, nb, fh * fw * e->A, e->rpn.post_nms_top_n);
     if (e->with_rcnn) {
       nms_workspace_alloc(e->ws_det, nb * e->num_classes, e->rpn.post_nms_top_n, e->det.class_max);
-      const size_t fcap = (size_t)e->num_classes * e->det.class_max;
-      LUMI_CUDA_CHECK(cudaMalloc(&e->d_final_keys, ((size_t)nb * fcap * 2 + nb) * sizeof(float)));
+      LUMI_CUDA_CHECK(cudaMalloc(&e->d_final_keys, det_final_scratch_bytes(nb, e->num_classes, e->det.class_max)));
     }
   } else {
     LUMI_CUDA_CHECK(cudaMalloc(&e->d_ssd_anchors, e->ssd_anchor_host.size() * sizeof(float)));
     LUMI_CUDA_CHECK(cudaMemcpy(e->d_ssd_anchors, e->ssd_anchor_host.data(), e->ssd_anchor_host.size() * sizeof(float),
                                cudaMemcpyHostToDevice));
     nms_workspace_alloc(e->ws_det, nb * e->num_classes, e->ssd_total_anchors, e->det.class_max);
-    const size_t fcap = (size_t)e->num_classes * e->det.class_max;
-    LUMI_CUDA_CHECK(cudaMalloc(&e->d_final_keys, ((size_t)nb * fcap * 2 + nb) * sizeof(float)));
+    LUMI_CUDA_CHECK(cudaMalloc(&e->d_final_keys, det_final_scratch_bytes(nb, e->num_classes, e->det.class_max)));
   }
   e->finalized = true;
   return LUMI_OK;

@@ -65,6 +65,7 @@ struct DetParams {
   int prob_stride;        // floats between consecutive rows of cls_prob (>= nc+1)
   int delta_stride;       // floats between consecutive rows of deltas
 };
+size_t det_final_scratch_bytes(int nimg, int nc, int class_max);   // size of `final_keys` below
 // boxes_in [nimg][r][4] (or shared anchors when boxes_img_stride == 0), row_counts [nimg] or nullptr
 void launch_class_detections(const float* boxes_in, long boxes_img_stride, const int* row_counts, const float* deltas,
                              const float* cls_prob, int nimg, const DetParams& p, NmsWorkspace& ws, float* final_keys,

@@ -180,8 +180,7 @@ int lumi_op_class_detections(const float* boxes_in, const float* deltas, const f
   NmsWorkspace ws;
   struct G { NmsWorkspace& w; ~G() { nms_workspace_free(w); } } g{ws};
   nms_workspace_alloc(ws, nc, r, class_max);
-  const size_t fcap = (size_t)nc * class_max;
-  DevBuf fk((fcap * 2 + 1) * sizeof(float));
+  DevBuf fk(det_final_scratch_bytes(1, nc, class_max));
   DetParams p{};
   p.r = r; p.nc = nc; p.im_h = im_h; p.im_w = im_w; p.var0 = var0; p.var1 = var1; p.min_prob = min_prob;
   p.nms_threshold = nms_threshold; p.class_max = class_max; p.total_max = total_max;

@@ -68,7 +68,7 @@ __device__ __forceinline__ bool iou_gt(float4 a, float4 b, float thr) {
 // ------------------------------------------------------------------ workspace
 void nms_workspace_alloc(NmsWorkspace& ws, int problems, int cap, int max_out) {
   ws.problems = problems; ws.cap = cap; ws.max_out = max_out;
-  ws.words = cdiv(cap, 64);
+  ws.words = (cdiv(cap, 64) + 1) & ~1;      // even: mask rows stay 16 B aligned for cp.async.bulk
   size_t pc = (size_t)problems * cap;
   LUMI_CUDA_CHECK(cudaMalloc(&ws.keys, pc * sizeof(float)));
   LUMI_CUDA_CHECK(cudaMalloc(&ws.boxes, pc * 4 * sizeof(float)));
@@ -79,8 +79,7 @@ void nms_workspace_alloc(NmsWorkspace& ws, int problems, int cap, int max_out) {
   LUMI_CUDA_CHECK(cudaMalloc(&ws.mask, pc * ws.words * sizeof(unsigned long long)));
   LUMI_CUDA_CHECK(cudaMalloc(&ws.keep, (size_t)problems * max_out * sizeof(int)));
   LUMI_CUDA_CHECK(cudaMalloc(&ws.nkeep, problems * sizeof(int)));
-  int p2 = 1; while (p2 < cap) p2 <<= 1;
-  if (p2 > 32768) LUMI_CUDA_CHECK(cudaMalloc(&ws.sort_tmp, (size_t)problems * p2 * sizeof(unsigned long long)));
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.sort_tmp, (size_t)problems * 2 * cap * sizeof(unsigned long long)));   // radix ping-pong
 }
 void nms_workspace_free(NmsWorkspace& ws) {
   cudaFree(ws.keys); cudaFree(ws.boxes); cudaFree(ws.order); cudaFree(ws.nvalid); cudaFree(ws.sboxes);
@@ -171,34 +170,132 @@ __global__ void __launch_bounds__(1024) sort_desc_gmem_kernel(const float* __res
     order[(size_t)p * cap + r] = (int)(0xFFFFFFFFu - (uint32_t)(v[r] & 0xFFFFFFFFull));
 }
 
+// ------------------------------------------------------------------ LSD radix sort (one CTA per problem)
+// Stable 4 x 8-bit passes over (key', index) pairs, key' = ~score_key: ascending key' == descending
+// score, stability == "ties -> lower index first" (tf.nn.top_k / NMS candidate order).  Each warp owns a
+// contiguous segment and walks it 32 items at a time; __match_any_sync gives the rank among equal
+// digits inside the round, a per-warp digit table in shared memory the rank across rounds, and one
+// block-wide exclusive scan in digit-major order the global offsets.  Two sweeps per pass (count, then
+// scatter) keep register use independent of the problem size; data ping-pongs through L2.
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const float* __restrict__ keys, int cap,
+                                                                     const int* __restrict__ n_in, int topn,
+                                                                     unsigned long long* __restrict__ tmp,
+                                                                     int* __restrict__ order,
+                                                                     int* __restrict__ nvalid) {
+  __shared__ uint32_t hist[NWARPS][256];
+  __shared__ uint32_t warp_tot[NWARPS];
+  __shared__ int s_count;
+  const int p = blockIdx.x;
+  const int n = n_in ? min(n_in[p], cap) : cap;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  unsigned long long* bufA = tmp + (size_t)p * 2 * cap;
+  unsigned long long* bufB = bufA + cap;
+  const int seg = ((n + NWARPS - 1) / NWARPS + 31) & ~31;       // items per warp, multiple of 32
+  const int lo = warp * seg, hi = min(n, lo + seg);
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  int local_valid = 0;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = pass * 8;
+    const unsigned long long* src = (pass & 1) ? bufB : bufA;
+    unsigned long long* dst = (pass & 1) ? bufA : bufB;
+    for (int d = lane; d < 256; d += 32) hist[warp][d] = 0;
+    __syncwarp();
+    // ---- sweep 1: per-warp digit counts
+    for (int base = lo; base < hi; base += 32) {
+      const int i = base + lane;
+      const bool act = i < hi;
+      unsigned long long v = 0;
+      if (act) {
+        if (pass == 0) {
+          const uint32_t k = score_key(keys[(size_t)p * cap + i]);
+          local_valid += k != 0;
+          v = ((unsigned long long)(~k) << 32) | (uint32_t)i;
+        } else {
+          v = src[i];
+        }
+      }
+      const uint32_t digit = (uint32_t)(v >> (32 + shift)) & 255u;
+      const uint32_t amask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const uint32_t peers = __match_any_sync(amask, digit);
+        if ((peers & lt_mask) == 0) hist[warp][digit] += __popc(peers);      // leader of its digit group
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // ---- exclusive scan in digit-major order: entry j = d * NWARPS + w, 8 entries per thread
+    {
+      uint32_t v[8], sum = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int j = threadIdx.x * 8 + e;
+        v[e] = hist[j % NWARPS][j / NWARPS];
+        sum += v[e];
+      }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+      __syncthreads();
+      uint32_t wbase = 0;
+      for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
+      uint32_t run = wbase + incl - sum;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int j = threadIdx.x * 8 + e;
+        hist[j % NWARPS][j / NWARPS] = run;
+        run += v[e];
+      }
+    }
+    __syncthreads();
+    // ---- sweep 2: stable scatter
+    for (int base = lo; base < hi; base += 32) {
+      const int i = base + lane;
+      const bool act = i < hi;
+      unsigned long long v = 0;
+      if (act) {
+        if (pass == 0) {
+          const uint32_t k = score_key(keys[(size_t)p * cap + i]);
+          v = ((unsigned long long)(~k) << 32) | (uint32_t)i;
+        } else {
+          v = src[i];
+        }
+      }
+      const uint32_t digit = (uint32_t)(v >> (32 + shift)) & 255u;
+      const uint32_t amask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const uint32_t peers = __match_any_sync(amask, digit);
+        const uint32_t old = hist[warp][digit];
+        const uint32_t pos = old + __popc(peers & lt_mask);
+        __syncwarp(amask);
+        if ((peers & lt_mask) == 0) hist[warp][digit] = old + __popc(peers);
+        if (pass < 3) {
+          dst[pos] = v;
+        } else if ((int)pos < topn && (uint32_t)(v >> 32) != 0xFFFFFFFFu) {
+          order[(size_t)p * cap + pos] = (int)(uint32_t)v;                    // final pass: sorted indices
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+  atomicAdd(&s_count, local_valid);
+  __syncthreads();
+  if (threadIdx.x == 0) nvalid[p] = min(s_count, topn);
+}
+
 static void run_sort(const float* keys, int problems, int cap, const int* n_in, int topn, int* order, int* nvalid,
                      unsigned long long* tmp, cudaStream_t st) {
   if (!problems || !cap) return;
-  int p2 = 2;
-  while (p2 < cap) p2 <<= 1;
-  if (p2 <= 16384) {
-    size_t smem = (size_t)p2 * 8;
-    static bool set32 = false;
-    if (!set32) {
-      LUMI_CUDA_CHECK(cudaFuncSetAttribute(sort_desc_smem_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           16384 * 8));
-      set32 = true;
-    }
-    int threads = p2 / 2 < 1024 ? (p2 / 2 < 32 ? 32 : p2 / 2) : 1024;
-    sort_desc_smem_kernel<uint32_t><<<problems, threads, smem, st>>>(keys, cap, p2, n_in, topn, order, nvalid);
-  } else if (p2 <= 32768) {
-    size_t smem = (size_t)p2 * 6;
-    static bool set16 = false;
-    if (!set16) {
-      LUMI_CUDA_CHECK(cudaFuncSetAttribute(sort_desc_smem_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           32768 * 6));
-      set16 = true;
-    }
-    sort_desc_smem_kernel<uint16_t><<<problems, 1024, smem, st>>>(keys, cap, p2, n_in, topn, order, nvalid);
-  } else {
-    LUMI_REQUIRE(tmp != nullptr, "sort: no global scratch for > 32768 candidates");
-    sort_desc_gmem_kernel<<<problems, 1024, 0, st>>>(keys, cap, p2, n_in, topn, tmp, order, nvalid);
-  }
+  LUMI_REQUIRE(tmp != nullptr, "sort: missing scratch");
+  if (cap > 4096) sort_desc_radix_kernel<32><<<problems, 1024, 0, st>>>(keys, cap, n_in, topn, tmp, order, nvalid);
+  else sort_desc_radix_kernel<8><<<problems, 256, 0, st>>>(keys, cap, n_in, topn, tmp, order, nvalid);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
@@ -217,6 +314,35 @@ __global__ void gather_sorted_kernel(const float* __restrict__ boxes, const floa
 }
 
 // ------------------------------------------------------------------ NMS bitmask matrix
+// Normalised box (min/max corners + area) exactly as TF's IOU() computes them.
+struct NBox { float ymin, xmin, ymax, xmax, area; };
+__device__ __forceinline__ NBox normalise_box(float4 b) {
+  NBox n;
+  n.ymin = fminf(b.y, b.w); n.xmin = fminf(b.x, b.z); n.ymax = fmaxf(b.y, b.w); n.xmax = fmaxf(b.x, b.z);
+  n.area = __fmul_rn(__fsub_rn(n.ymax, n.ymin), __fsub_rn(n.xmax, n.xmin));
+  return n;
+}
+// Same decision as iou_gt() on pre-normalised boxes, for thr >= 0, with the cheap rejections first:
+// no x- or y-overlap => inter == 0 => iou == 0 => not > thr.
+__device__ __forceinline__ bool iou_gt_norm(const NBox& a, const NBox& b, float thr) {
+  const float ix0 = fmaxf(a.xmin, b.xmin), ix1 = fminf(a.xmax, b.xmax);
+  const float dx = __fsub_rn(ix1, ix0);
+  if (!(dx > 0.f)) return false;
+  const float iy0 = fmaxf(a.ymin, b.ymin), iy1 = fminf(a.ymax, b.ymax);
+  const float dy = __fsub_rn(iy1, iy0);
+  if (!(dy > 0.f)) return false;
+  if (a.area <= 0.f || b.area <= 0.f) return false;
+  const float inter = __fmul_rn(dy, dx);              // == max(dy,0)*max(dx,0) here
+  const float uni = __fsub_rn(__fadd_rn(a.area, b.area), inter);
+  if (inter == 0.f && uni > 0.f) return false;        // product underflowed to 0: iou == 0
+  if (thr > 0.f && uni > 1e-30f && uni < 1e30f && inter < 1e30f) {
+    const float t = __fmul_rn(thr, uni);
+    if (inter < __fmul_rn(t, 0.99999905f)) return false;
+    if (inter > __fmul_rn(t, 1.00000095f)) return true;
+  }
+  return __fdiv_rn(inter, uni) > thr;
+}
+
 // grid (pair slot, problem); 64 threads; a block walks the upper-triangle (row block, col block) pairs
 // of its problem with a grid stride, so launch cost follows the live candidate count, not the capacity.
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sboxes, const int* __restrict__ nvalid,
@@ -227,6 +353,7 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   const int nw = (n + 63) >> 6;
   const long npairs = (long)nw * (nw + 1) / 2;
   __shared__ float4 cbox[64];
+  __shared__ NBox cnorm[64];
   const float4* B = reinterpret_cast<const float4*>(sboxes) + (size_t)p * cap;
   const int t = threadIdx.x;
   for (long pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
@@ -239,16 +366,23 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
     while ((long)(rb + 1) * (2 * nw - rb) / 2 <= pr) ++rb;
     const int cb = rb + (int)(pr - (long)rb * (2 * nw - rb + 1) / 2);
     __syncthreads();
-    if (cb * 64 + t < n) cbox[t] = B[cb * 64 + t];
+    if (cb * 64 + t < n) { cbox[t] = B[cb * 64 + t]; cnorm[t] = normalise_box(cbox[t]); }
     __syncthreads();
     const int i = rb * 64 + t;
     if (i >= n) continue;
     const float4 bi = B[i];
     unsigned long long bits = 0ull;
     const int jmax = min(64, n - cb * 64);
-    for (int j = 0; j < jmax; ++j) {
-      const int col = cb * 64 + j;
-      if (col > i && iou_gt(bi, cbox[j], thr)) bits |= 1ull << j;
+    if (thr >= 0.f) {
+      const NBox ni = normalise_box(bi);
+      const int j0 = (cb == rb) ? t + 1 : 0;           // only columns > i
+      for (int j = j0; j < jmax; ++j)
+        if (iou_gt_norm(ni, cnorm[j], thr)) bits |= 1ull << j;
+    } else {                                            // negative thresholds: generic (exact) path
+      for (int j = 0; j < jmax; ++j) {
+        const int col = cb * 64 + j;
+        if (col > i && iou_gt(bi, cbox[j], thr)) bits |= 1ull << j;
+      }
     }
     mask[((size_t)p * cap + i) * words + cb] = bits;
   }
@@ -319,6 +453,92 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long*
   if (threadIdx.x == 0) nkeep[p] = s_total;
 }
 
+// Staged variant: the mask rows of chunk c+1 (only the words >= c+1, the upper triangle) are bulk-copied
+// (cp.async.bulk -> mbarrier) into shared memory while chunk c is resolved, so the greedy walk never
+// waits on an L2 round trip: diag resolve and the OR of the kept rows both read shared memory.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256) nms_scan_staged_kernel(const unsigned long long* __restrict__ mask,
+                                                              const int* __restrict__ nvalid, int cap, int words,
+                                                              int max_out, int* __restrict__ keep,
+                                                              int* __restrict__ nkeep) {
+  extern __shared__ __align__(16) unsigned long long sm64[];
+  unsigned long long* removed = sm64;                         // [words]
+  unsigned long long* buf = sm64 + words;                     // [2][64][words]
+  __shared__ __align__(8) uint64_t full_bar[2];
+  __shared__ int s_kept[64];
+  __shared__ int s_nk, s_total, s_done;
+  const int p = blockIdx.x;
+  const int n = nvalid[p];
+  const int nw = (n + 63) >> 6;
+  const int nw_e = (nw + 1) & ~1;                             // 16 B granularity of the bulk copies
+  const unsigned long long* M = mask + (size_t)p * cap * words;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = 0ull;
+  if (threadIdx.x == 0) {
+    s_total = 0; s_done = (max_out <= 0 || n == 0) ? 1 : 0;
+    mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int c) {             // rows of chunk c, words [c_e, nw_e) -> buf[c & 1]; threads 0..63
+    const int c_e = c & ~1;
+    const int rows = min(64, n - c * 64);
+    const uint32_t row_bytes = (uint32_t)(nw_e - c_e) * 8u;
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(&full_bar[c & 1], row_bytes * (uint32_t)rows);
+    if ((int)threadIdx.x < rows)
+      bulk_g2s(buf + ((size_t)(c & 1) * 64 + threadIdx.x) * words, M + (size_t)(c * 64 + threadIdx.x) * words + c_e,
+               row_bytes, &full_bar[c & 1]);
+  };
+  const bool done0 = s_done != 0;
+  int last_issued = -1, last_waited = -1;                     // uniform across the CTA
+  if (!done0 && nw > 0) {
+    if (threadIdx.x < 64) issue(0);
+    last_issued = 0;
+  }
+  for (int c = 0; c < nw && !done0; ++c) {
+    const int c_e = c & ~1;
+    mbar_wait(&full_bar[c & 1], ((uint32_t)c >> 1) & 1u);
+    last_waited = c;
+    if (c + 1 < nw) {                                         // buf[(c+1)&1] was last read in iteration c-1
+      if (threadIdx.x < 64) { fence_proxy_async(); issue(c + 1); }
+      last_issued = c + 1;
+    }
+    const unsigned long long* rows = buf + (size_t)(c & 1) * 64 * words;
+    if (threadIdx.x == 0) {
+      unsigned long long cur = removed[c];
+      const int lim = min(64, n - c * 64);
+      const unsigned long long vmask = lim == 64 ? ~0ull : ((1ull << lim) - 1ull);
+      unsigned long long avail = ~cur & vmask;
+      int nk = 0, total = s_total;
+      while (avail) {
+        const int b = __ffsll((long long)avail) - 1;
+        s_kept[nk++] = b;
+        keep[(size_t)p * max_out + total] = c * 64 + b;
+        if (++total >= max_out) { s_done = 1; break; }
+        cur |= rows[(size_t)b * words + (c - c_e)];
+        avail = ~cur & vmask & ~((2ull << b) - 1ull);
+      }
+      s_nk = nk; s_total = total;
+    }
+    __syncthreads();
+    if (s_done) break;
+    const int nk = s_nk;
+    for (int w = c + 1 + threadIdx.x; w < nw; w += blockDim.x) {
+      unsigned long long acc = removed[w];
+      for (int i = 0; i < nk; ++i) acc |= rows[(size_t)s_kept[i] * words + (w - c_e)];
+      removed[w] = acc;
+    }
+    __syncthreads();
+  }
+  // never exit with a bulk copy still landing in this CTA's shared memory
+  if (last_issued > last_waited) mbar_wait(&full_bar[last_issued & 1], ((uint32_t)last_issued >> 1) & 1u);
+  if (threadIdx.x == 0) nkeep[p] = s_total;
+}
+
 static void run_nms(NmsWorkspace& ws, int problems, float thr, int max_out, cudaStream_t st) {
   if (!problems) return;
   long maxpairs = (long)ws.words * (ws.words + 1) / 2;
@@ -326,8 +546,20 @@ static void run_nms(NmsWorkspace& ws, int problems, float thr, int max_out, cuda
   nms_mask_kernel<<<grid, 64, 0, st>>>(ws.sboxes, ws.nvalid, ws.cap, ws.words, thr, ws.mask);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
-  size_t smem = (size_t)ws.words * sizeof(unsigned long long);
-  nms_scan_kernel<<<problems, 256, smem, st>>>(ws.mask, ws.nvalid, ws.cap, ws.words, max_out, ws.keep, ws.nkeep);
+  const size_t staged_smem = ((size_t)ws.words + 2 * 64 * (size_t)ws.words) * sizeof(unsigned long long);
+  if (staged_smem <= 200 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      LUMI_CUDA_CHECK(cudaFuncSetAttribute(nms_scan_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024));
+      attr = true;
+    }
+    nms_scan_staged_kernel<<<problems, 256, staged_smem, st>>>(ws.mask, ws.nvalid, ws.cap, ws.words, max_out, ws.keep,
+                                                              ws.nkeep);
+  } else {
+    size_t smem = (size_t)ws.words * sizeof(unsigned long long);
+    nms_scan_kernel<<<problems, 256, smem, st>>>(ws.mask, ws.nvalid, ws.cap, ws.words, max_out, ws.keep, ws.nkeep);
+  }
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
@@ -412,6 +644,11 @@ void launch_rpn_proposals(const float* cls, const float* box, long img_stride_cl
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
 
+size_t det_final_scratch_bytes(int nimg, int nc, int class_max) {
+  const size_t fcap = (size_t)nc * class_max;
+  return (size_t)nimg * fcap * 8 + (size_t)nimg * 4 + 16 + (size_t)nimg * 2 * fcap * sizeof(unsigned long long);
+}
+
 // ------------------------------------------------------------------ per-class detection chain
 __global__ void det_decode_kernel(const float* __restrict__ boxes_in, long boxes_img_stride,
                                   const int* __restrict__ row_counts, const float* __restrict__ deltas,
@@ -475,7 +712,8 @@ __global__ void det_output_kernel(const float* __restrict__ sboxes, const float*
   labels[(size_t)img * total_max + k] = lab;
 }
 
-// final_keys: scratch [nimg][nc*class_max] floats followed by int order [same] and int nvalid[nimg]
+// final_keys: scratch of det_final_scratch_bytes(): [nimg][nc*class_max] float keys, int order [same],
+// int nvalid[nimg], then the radix ping-pong buffers
 void launch_class_detections(const float* boxes_in, long boxes_img_stride, const int* row_counts, const float* deltas,
                              const float* cls_prob, int nimg, const DetParams& p, NmsWorkspace& ws, float* final_keys,
                              float* objects, int* labels, float* probs, int* counts, cudaStream_t st) {
@@ -500,11 +738,13 @@ void launch_class_detections(const float* boxes_in, long boxes_img_stride, const
   float* fkeys = final_keys;
   int* forder = reinterpret_cast<int*>(final_keys + (size_t)nimg * fcap);
   int* fnvalid = forder + (size_t)nimg * fcap;
+  unsigned long long* fscratch = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(fnvalid + nimg) + 15) & ~(uintptr_t)15);
   dim3 g3(cdiv(p.class_max, 128), P);
   det_concat_kernel<<<g3, 128, 0, st>>>(ws.sscores, ws.keep, ws.nkeep, p.nc, ws.cap, p.class_max, fkeys);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
-  run_sort(fkeys, nimg, fcap, nullptr, p.total_max, forder, fnvalid, nullptr, st);
+  run_sort(fkeys, nimg, fcap, nullptr, p.total_max, forder, fnvalid, fscratch, st);
   dim3 g4(cdiv(p.total_max, 128), nimg);
   det_output_kernel<<<g4, 128, 0, st>>>(ws.sboxes, ws.sscores, ws.keep, forder, fnvalid, p.nc, ws.cap, p.class_max,
                                         p.total_max, objects, labels, probs, counts);
