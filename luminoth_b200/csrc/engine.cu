@@ -677,13 +677,15 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   Act pooled, feat;
   if (need_pooled) pooled = cx.act(n * post, e->pooled_w, e->pooled_h, fmap.c);
   if (fuse_mean) feat = cx.act(n * post, 1, 1, fmap.c);
+  float* fmap_f32 = cx.f32(fmap.numel());                                  // gather source of the ROI kernel
   if (!cx.dry) {
     // algorithmic bytes: feature map once + rois + output (fp16x2 planes = 4 B / element)
     const double bytes = 4.0 * fmap.numel() + 16.0 * n * post + 4.0 * (double)(need_pooled ? pooled.numel() : 0) +
                          4.0 * (double)(fuse_mean ? feat.numel() : 0);
     ProfScope ps(cx.e, cx.dry, PC_ROI, bytes);
-    launch_roi_pool(fmap, proposals, e->d_prop_counts, post, (float)h, (float)w, e->pooled_h, e->pooled_w, pooled,
-                    fuse_mean ? feat : Act(), cx.st);
+    launch_act_to_f32(fmap, fmap_f32, cx.st);
+    launch_roi_pool(fmap_f32, fmap.n, fmap.h, fmap.w, fmap.c, proposals, e->d_prop_counts, post, (float)h, (float)w,
+                    e->pooled_h, e->pooled_w, pooled, fuse_mean ? feat : Act(), cx.st);
   }
   if (need_pooled) cx.tap_act("roi_pool", pooled);
   if (!fuse_mean) {

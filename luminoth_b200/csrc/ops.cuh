@@ -19,8 +19,9 @@ void launch_frcnn_anchors(const int* ref /*A x 4*/, int A, int fh, int fw, int s
 // ---- ROI crop + 2x2 max pool (roi.cu) : roi_pool.py:68-95
 // rois [nimg][rmax][4] (x1,y1,x2,y2 px), counts [nimg] (nullptr -> all rmax valid); out (nimg*rmax, pw, ph, C)
 // and/or mean (nimg*rmax, 1, 1, C) = tf.reduce_mean over the pooled cells (either may be an empty Act).
-void launch_roi_pool(Act fmap, const float* rois, const int* counts, int rmax, float im_h, float im_w, int ph, int pw,
-                     Act out, Act mean, cudaStream_t st);
+// fmap_f32: fp32 NHWC copy of the feature map (n, fh, fw, c).
+void launch_roi_pool(const float* fmap_f32, int n, int fh, int fw, int c, const float* rois, const int* counts, int rmax,
+                     float im_h, float im_w, int ph, int pw, Act out, Act mean, cudaStream_t st);
 
 // ---- proposal / detection chains (postproc.cu)
 struct NmsWorkspace {

@@ -113,9 +113,8 @@ int lumi_op_roi_pool(const float* fmap, int n, int fh, int fw, int c, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   LUMI_REQUIRE(n == 1 || roi_batch == nullptr, "roi_pool op: single image (roi_batch must be NULL or n == 1)");
   (void)roi_batch;
-  ActBuf in(n, fh, fw, c), out(r, pw, ph, c);
-  launch_f32_to_act(fmap, in.a, st);
-  launch_roi_pool(in.a, rois, nullptr, r, im_h, im_w, ph, pw, out.a, Act(), st);
+  ActBuf out(r, pw, ph, c);
+  launch_roi_pool(fmap, n, fh, fw, c, rois, nullptr, r, im_h, im_w, ph, pw, out.a, Act(), st);
   launch_act_to_f32(out.a, y, st);
   LUMI_CUDA_CHECK(cudaStreamSynchronize(st));
   return LUMI_OK;
