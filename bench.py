@@ -277,10 +277,13 @@ def run_ours(args, wl):
                     'ms_per_step': tc_ms / args.steps,
                     'note': 'fp32-class accuracy is bought with 3 kind::f16 MMAs per algorithmic MAC '
                             '(fp16x2 operand split): the tensor pipe does 3x the algorithmic FLOPs, so frac <= 1/3'}
-            rs, rms, rbytes = prof['roi_pool']
-            if rms > 0:
-                roof['roi_pool_hbm'] = {'achieved_GBs': rbytes / (rms * 1e-3) / 1e9, 'peak_GBs': hbm,
-                                        'frac': rbytes / (rms * 1e-3) / 1e9 / hbm}
+            for cat, key, note in (('roi_pool', 'roi_pool_hbm', 'ROI crop+max-pool(+mean) kernel; gather is L1/issue-bound, not HBM-bound'),
+                                   ('rpn_proposals', 'rpn_nms_hbm', 'RPN decode+sort+bitmask NMS chain (bitmask-algorithm bytes)')):
+                rs, rms, rbytes = prof.get(cat, (0, 0.0, 0.0))
+                if rms > 0 and rbytes > 0:
+                    roof[key] = {'achieved_GBs': rbytes / (rms * 1e-3) / 1e9, 'peak_GBs': hbm,
+                                 'frac': rbytes / (rms * 1e-3) / 1e9 / hbm, 'ms_per_step': rms / args.steps,
+                                 'algorithmic_MB_per_step': rbytes / args.steps / 1e6, 'note': note}
         out = {
             'metric': 'images/sec', 'value': v, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',

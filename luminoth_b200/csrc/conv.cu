@@ -198,6 +198,7 @@ void launch_conv_simt(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
 // =====================================================================================
 struct TcArgs {
   CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+  CUtensorMap tm_o_hi, tm_o_lo;    // output planes, box {32 ch, tw, th, nb}, SWIZZLE_64B (split outputs only)
   const float* scale; const float* bias;
   __half* out_hi; __half* out_lo; float* out_f32;
   const __half* res_hi; const __half* res_lo;
@@ -225,7 +226,8 @@ template <int BN, int STAGES>
 struct TcCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int OUT_STAGE_BYTES = 2 * 2 * 128 * 64;   // per column half: hi + lo slabs of 128 rows x 32 ch
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 4 * BN;          // D1[0], D1[1], D2[0], D2[1]  (256 or 512 columns)
 };
 
@@ -241,7 +243,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   using Cfg = TcCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES;      // [2 halves][hi, lo][128 rows x 64 B], 64 B swizzle
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + Cfg::OUT_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full_bar = empty_bar + STAGES;       // [2]  D1[buf] chunk complete (tcgen05.commit)
   uint64_t* acc_empty_bar = acc_full_bar + 2;        // [2]  D1[buf] drained by the 8 epilogue warps
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tm_a_hi); tma_prefetch_desc(&a.tm_a_lo);
     tma_prefetch_desc(&a.tm_b_hi); tma_prefetch_desc(&a.tm_b_lo);
+    if (!a.out_f32) { tma_prefetch_desc(&a.tm_o_hi); tma_prefetch_desc(&a.tm_o_lo); }
   }
   if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
@@ -408,38 +412,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
 
       // ---- scale/bias (folded BN) -> +residual -> activation -> store (overlaps the next tile's MMAs)
-      if (valid) {
+      // split outputs: each column half (4 warps) stages a 128 x 32-channel slab per plane in shared
+      // memory (64 B swizzle) and one thread issues the two bulk tensor stores -- fully coalesced, and
+      // TMA clips partial tiles; fp32 outputs (head layers) are written directly.
+      uint8_t* st_hi = out_stage + half * (Cfg::OUT_STAGE_BYTES / 2);
+      uint8_t* st_lo = st_hi + 128 * 64;
+      const bool store_leader = ((warp - 2) & 3) == 0 && lane == 0;     // one issuing thread per column half
 #pragma unroll
-        for (int ch = 0; ch < HC / 32; ++ch) {
-          const int c0 = n0 + ch * 32;
-          if (c0 < a.cout) {
-            float v[32];
-            const bool full = (c0 + 32 <= a.cout);
-            // scale / bias vectors are padded to cout_pad: 16 B loads are always in bounds
+      for (int ch = 0; ch < HC / 32; ++ch) {
+        const int c0 = n0 + ch * 32;
+        if (c0 < a.cout) {                               // uniform over the 4 warps of this column half
+          float v[32];
+          const bool full = (c0 + 32 <= a.cout);
+          // scale / bias vectors are padded to cout_pad: 16 B loads are always in bounds
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + c0) + g);
-              const float4 bi = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + g);
-              v[g * 4 + 0] = fmaf(racc[ch * 32 + g * 4 + 0], sc.x, bi.x);
-              v[g * 4 + 1] = fmaf(racc[ch * 32 + g * 4 + 1], sc.y, bi.y);
-              v[g * 4 + 2] = fmaf(racc[ch * 32 + g * 4 + 2], sc.z, bi.z);
-              v[g * 4 + 3] = fmaf(racc[ch * 32 + g * 4 + 3], sc.w, bi.w);
+          for (int g = 0; g < 8; ++g) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + c0) + g);
+            const float4 bi = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + g);
+            v[g * 4 + 0] = fmaf(racc[ch * 32 + g * 4 + 0], sc.x, bi.x);
+            v[g * 4 + 1] = fmaf(racc[ch * 32 + g * 4 + 1], sc.y, bi.y);
+            v[g * 4 + 2] = fmaf(racc[ch * 32 + g * 4 + 2], sc.z, bi.z);
+            v[g * 4 + 3] = fmaf(racc[ch * 32 + g * 4 + 3], sc.w, bi.w);
+          }
+          if (a.res_hi && valid) {     // residual tensors always have cout % 32 == 0 channels
+            const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + rpix * a.cout + c0);
+            const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + rpix * a.cout + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
+              const __half* ph = reinterpret_cast<const __half*>(&h4);
+              const __half* pl = reinterpret_cast<const __half*>(&l4);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] += join_f16(ph[j], pl[j]);
             }
-            if (a.res_hi) {     // residual tensors always have cout % 32 == 0 channels
-              const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + rpix * a.cout + c0);
-              const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + rpix * a.cout + c0);
+          }
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
-                const __half* ph = reinterpret_cast<const __half*>(&h4);
-                const __half* pl = reinterpret_cast<const __half*>(&l4);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[g * 8 + j] += join_f16(ph[j], pl[j]);
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
-            if (a.out_f32) {
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
+          if (a.out_f32) {
+            if (valid) {
               float* op = a.out_f32 + opix * a.cout + c0;
               if (full && (a.cout % 4) == 0) {
 #pragma unroll
@@ -450,26 +460,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 for (int j = 0; j < 32; ++j)
                   if (c0 + j < a.cout) op[j] = v[j];
               }
-            } else {            // split outputs always have cout % 32 == 0
-              bool ovf = false;
-              uint4 hv[4], lv[4];
-              __half* ph = reinterpret_cast<__half*>(hv);
-              __half* pl = reinterpret_cast<__half*>(lv);
+            }
+          } else {            // split outputs always have cout % 32 == 0
+            bool ovf = false;
+            uint4 hv[4], lv[4];
+            __half* ph = reinterpret_cast<__half*>(hv);
+            __half* pl = reinterpret_cast<__half*>(lv);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                ovf |= !(fabsf(v[j]) <= LUMI_F16_MAX);
-                split_f32(v[j], ph[j], pl[j]);
-              }
-              uint4* oh = reinterpret_cast<uint4*>(a.out_hi + opix * a.cout + c0);
-              uint4* ol = reinterpret_cast<uint4*>(a.out_lo + opix * a.cout + c0);
+            for (int j = 0; j < 32; ++j) {
+              ovf |= !(fabsf(v[j]) <= LUMI_F16_MAX);
+              split_f32(v[j], ph[j], pl[j]);
+            }
+            if (ovf && valid && a.overflow) atomicOr(a.overflow, 1);
+            if (store_leader) bulk_wait_group_read0();   // the previous slab's stores have drained the staging
+            named_bar_sync(1 + half, 128);
+            const int sw = (row >> 1) & 3;               // SWIZZLE_64B: 16 B chunk index ^= address bits [7:8]
 #pragma unroll
-              for (int g = 0; g < 4; ++g) { oh[g] = hv[g]; ol[g] = lv[g]; }
-              if (ovf && a.overflow) atomicOr(a.overflow, 1);
+            for (int g = 0; g < 4; ++g) {
+              *reinterpret_cast<uint4*>(st_hi + row * 64 + ((g ^ sw) << 4)) = hv[g];
+              *reinterpret_cast<uint4*>(st_lo + row * 64 + ((g ^ sw) << 4)) = lv[g];
+            }
+            fence_proxy_async();
+            named_bar_sync(1 + half, 128);
+            if (store_leader) {
+              tma_store_4d(&a.tm_o_hi, st_hi, c0, x0, y0, img0);
+              tma_store_4d(&a.tm_o_lo, st_lo, c0, x0, y0, img0);
+              bulk_commit_group();
             }
           }
         }
       }
     }
+    if (((warp - 2) & 3) == 0 && lane == 0) bulk_wait_group0();   // all output stores complete before exit
   }
   tc_fence_before();
   __syncthreads();
@@ -516,6 +538,20 @@ static CUtensorMap make_map_act(const __half* base, int n, int h, int w, int c, 
   return m;
 }
 
+// output plane: box {32 ch, tw, th, nb}, 64 B swizzle (matches the epilogue's staging layout)
+static CUtensorMap make_map_out(const __half* base, int n, int h, int w, int c, int nb, int th, int tw) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(-2, "cuTensorMapEncodeTiled(output) failed: " + std::to_string((int)r));
+  return m;
+}
+
 static CUtensorMap make_map_wgt(const __half* base, int rows, int kdim, int bn) {
   CUtensorMap m;
   cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
@@ -547,6 +583,15 @@ static CUtensorMap cached_act_map(const __half* base, int n, int h, int w, int c
   if (it != g_map_cache.end()) return it->second;
   if (g_map_cache.size() > 4096) g_map_cache.clear();
   CUtensorMap m = make_map_act(base, n, h, w, c, nb, th, tw, stride, pix_pitch, row_pitch, img_pitch);
+  g_map_cache[k] = m;
+  return m;
+}
+static CUtensorMap cached_out_map(const __half* base, int n, int h, int w, int c, int nb, int th, int tw) {
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  MapKey k{base, n, h, w, -c, nb, th, tw};                 // negative c: output-map key space
+  auto it = g_map_cache.find(k);
+  if (it != g_map_cache.end()) return it->second;
+  CUtensorMap m = make_map_out(base, n, h, w, c, nb, th, tw);
   g_map_cache[k] = m;
   return m;
 }
@@ -630,6 +675,10 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   const int kdim = L.kh * L.kw * L.cin;
   a.tm_b_hi = cached_wgt_map(L.w_hi, L.cout_pad, kdim, bn);
   a.tm_b_lo = cached_wgt_map(L.w_lo, L.cout_pad, kdim, bn);
+  if (!io.out_f32) {
+    a.tm_o_hi = cached_out_map(io.out.hi, io.in.n, io.ho, io.wo, L.cout, nb, th, tw);
+    a.tm_o_lo = cached_out_map(io.out.lo, io.in.n, io.ho, io.wo, L.cout, nb, th, tw);
+  }
   a.scale = L.scale_tc; a.bias = L.bias;
   a.out_hi = io.out.hi; a.out_lo = io.out.lo; a.out_f32 = io.out_f32;
   a.res_hi = io.res.hi; a.res_lo = io.res.lo; a.res_h = io.res.h; a.res_w = io.res.w; a.res_stride = io.res_stride;

@@ -648,14 +648,17 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   float* pscores = cx.f32((size_t)n * post);
   if (!cx.dry) {
     LUMI_REQUIRE(na <= e->ws_rpn.cap, "image too large for the RPN workspace (max_h/max_w at lumi_create)");
-    ProfScope ps(cx.e, cx.dry, PC_RPN_POST);
+    // algorithmic bytes: decode N*(36 in + 20 out), sort N*4 + K*20, bitmask NMS K*16 + 2*K*ceil(K/64)*8 + P*4
+    const double kk = std::min(na, rp.pre_nms_top_n);
+    const double bytes = (double)n * (56.0 * na + 4.0 * na + 20.0 * kk + 16.0 * kk + 16.0 * kk * std::ceil(kk / 64.0) + 4.0 * post);
+    ProfScope ps(cx.e, cx.dry, PC_RPN_POST, bytes);
     launch_rpn_proposals(heads, heads, (long)fh * fw * hc, (long)fh * fw * hc, e->A, e->d_anchors, n, rp, e->ws_rpn,
                          proposals, pscores, e->d_prop_counts, cx.st);
   }
   cx.tap_f32("proposals", proposals, n, post, 4, 1);
   cx.tap_f32("proposal_scores", pscores, n, post, 1, 1);
   cx.tap_i32("proposal_counts", e->d_prop_counts, n);
-  cx.tap_f32("rpn_sorted_scores", e->ws_rpn.sscores, n, e->ws_rpn.cap, 1, 1);
+  cx.tap_f32("rpn_sorted_scores", e->ws_rpn.sscores, n, e->ws_rpn.ncap, 1, 1);
   cx.tap_i32("rpn_sorted_counts", e->ws_rpn.nvalid, n);
 
   if (!e->with_rcnn) {
@@ -964,7 +967,8 @@ int lumi_finalize(lumi_engine* e) {
     LUMI_CUDA_CHECK(cudaMemcpy(e->d_anchor_ref, e->anchor_ref.data(), e->anchor_ref.size() * sizeof(int),
                                cudaMemcpyHostToDevice));
     const int fh = cdiv(e->max_h, 16), fw = cdiv(e->max_w, 16);
-    nms_workspace_alloc(e->ws_rpn, nb, fh * fw * e->A, e->rpn.post_nms_top_n);
+    nms_workspace_alloc(e->ws_rpn, nb, fh * fw * e->A, e->rpn.post_nms_top_n,
+                        std::min(fh * fw * e->A, e->rpn.pre_nms_top_n));
     if (e->with_rcnn) {
       nms_workspace_alloc(e->ws_det, nb * e->num_classes, e->rpn.post_nms_top_n, e->det.class_max);
       LUMI_CUDA_CHECK(cudaMalloc(&e->d_final_keys, det_final_scratch_bytes(nb, e->num_classes, e->det.class_max)));

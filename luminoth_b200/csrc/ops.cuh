@@ -26,21 +26,22 @@ void launch_roi_pool(const float* fmap_f32, int n, int fh, int fw, int c, const 
 // ---- proposal / detection chains (postproc.cu)
 struct NmsWorkspace {
   // capacity: problems x cap candidates
-  int problems = 0, cap = 0;
+  int problems = 0, cap = 0;    // cap: candidates per problem before the top-n cut (decode / sort capacity)
+  int ncap = 0;                 // candidates per problem after the cut (sorted boxes / mask capacity), <= cap
   float* keys = nullptr;        // [P][cap]   score or -1 (invalid)
   float* boxes = nullptr;       // [P][cap][4] decoded (+clipped) boxes, input order
   int* order = nullptr;         // [P][cap]   sorted order (indices into input order)
   int* nvalid = nullptr;        // [P]        valid candidates (after top-n cut)
-  float* sboxes = nullptr;      // [P][cap][4] boxes in sorted order
-  float* sscores = nullptr;     // [P][cap]
-  unsigned long long* mask = nullptr;  // [P][cap][words]
+  float* sboxes = nullptr;      // [P][ncap][4] boxes in sorted order
+  float* sscores = nullptr;     // [P][ncap]
+  unsigned long long* mask = nullptr;  // [P][ncap][words]
   int words = 0;
   int* keep = nullptr;          // [P][max_out]
   int* nkeep = nullptr;         // [P]
   int max_out = 0;
   unsigned long long* sort_tmp = nullptr;  // global-memory sort scratch for cap > 32768
 };
-void nms_workspace_alloc(NmsWorkspace& ws, int problems, int cap, int max_out);
+void nms_workspace_alloc(NmsWorkspace& ws, int problems, int cap, int max_out, int ncap = 0);
 void nms_workspace_free(NmsWorkspace& ws);
 
 struct RpnParams {

@@ -157,7 +157,7 @@ int lumi_op_rpn_proposals(const float* cls_prob, const float* bbox_pred, const f
   LUMI_REQUIRE(na > 0 && pre_nms_top_n > 0 && post_nms_top_n > 0, "rpn_proposals: sizes must be positive");
   NmsWorkspace ws;
   struct G { NmsWorkspace& w; ~G() { nms_workspace_free(w); } } g{ws};
-  nms_workspace_alloc(ws, 1, na, post_nms_top_n);
+  nms_workspace_alloc(ws, 1, na, post_nms_top_n, pre_nms_top_n < na ? pre_nms_top_n : na);
   RpnParams p{};
   p.na = na; p.im_h = im_h; p.im_w = im_w; p.pre_nms_top_n = pre_nms_top_n; p.post_nms_top_n = post_nms_top_n;
   p.nms_threshold = nms_threshold; p.min_prob = min_prob; p.filter_outside = filter_outside;

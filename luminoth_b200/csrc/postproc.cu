@@ -66,17 +66,19 @@ __device__ __forceinline__ bool iou_gt(float4 a, float4 b, float thr) {
 }
 
 // ------------------------------------------------------------------ workspace
-void nms_workspace_alloc(NmsWorkspace& ws, int problems, int cap, int max_out) {
-  ws.problems = problems; ws.cap = cap; ws.max_out = max_out;
-  ws.words = (cdiv(cap, 64) + 1) & ~1;      // even: mask rows stay 16 B aligned for cp.async.bulk
+void nms_workspace_alloc(NmsWorkspace& ws, int problems, int cap, int max_out, int ncap) {
+  if (ncap <= 0 || ncap > cap) ncap = cap;
+  ws.problems = problems; ws.cap = cap; ws.max_out = max_out; ws.ncap = ncap;
+  ws.words = (cdiv(ncap, 64) + 1) & ~1;     // even: mask rows stay 16 B aligned for cp.async.bulk
   size_t pc = (size_t)problems * cap;
+  size_t pn = (size_t)problems * ncap;
   LUMI_CUDA_CHECK(cudaMalloc(&ws.keys, pc * sizeof(float)));
   LUMI_CUDA_CHECK(cudaMalloc(&ws.boxes, pc * 4 * sizeof(float)));
   LUMI_CUDA_CHECK(cudaMalloc(&ws.order, pc * sizeof(int)));
   LUMI_CUDA_CHECK(cudaMalloc(&ws.nvalid, problems * sizeof(int)));
-  LUMI_CUDA_CHECK(cudaMalloc(&ws.sboxes, pc * 4 * sizeof(float)));
-  LUMI_CUDA_CHECK(cudaMalloc(&ws.sscores, pc * sizeof(float)));
-  LUMI_CUDA_CHECK(cudaMalloc(&ws.mask, pc * ws.words * sizeof(unsigned long long)));
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.sboxes, pn * 4 * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.sscores, pn * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMalloc(&ws.mask, pn * ws.words * sizeof(unsigned long long)));
   LUMI_CUDA_CHECK(cudaMalloc(&ws.keep, (size_t)problems * max_out * sizeof(int)));
   LUMI_CUDA_CHECK(cudaMalloc(&ws.nkeep, problems * sizeof(int)));
   LUMI_CUDA_CHECK(cudaMalloc(&ws.sort_tmp, (size_t)problems * 2 * cap * sizeof(unsigned long long)));   // radix ping-pong
@@ -87,88 +89,9 @@ void nms_workspace_free(NmsWorkspace& ws) {
   ws = NmsWorkspace();
 }
 
-// ------------------------------------------------------------------ sort (one CTA per problem)
+// ------------------------------------------------------------------ sort keys
 // key' = bits(score)+1 for valid (score >= 0), 0 for invalid / padding; order: key' desc, index asc.
 __device__ __forceinline__ uint32_t score_key(float s) { return (s >= 0.f) ? (__float_as_uint(s) + 1u) : 0u; }
-
-template <typename IdxT>
-__global__ void __launch_bounds__(1024) sort_desc_smem_kernel(const float* __restrict__ keys, int cap, int cap_p2,
-                                                              const int* __restrict__ n_in, int topn,
-                                                              int* __restrict__ order, int* __restrict__ nvalid) {
-  extern __shared__ __align__(16) uint8_t sm[];
-  uint32_t* k = reinterpret_cast<uint32_t*>(sm);
-  IdxT* ix = reinterpret_cast<IdxT*>(sm + (size_t)cap_p2 * 4);
-  __shared__ int s_count;
-  const int p = blockIdx.x;
-  const int n = n_in ? min(n_in[p], cap) : cap;
-  if (threadIdx.x == 0) s_count = 0;
-  __syncthreads();
-  int local = 0;
-  for (int i = threadIdx.x; i < cap_p2; i += blockDim.x) {
-    uint32_t key = 0;
-    if (i < n) key = score_key(keys[(size_t)p * cap + i]);
-    k[i] = key; ix[i] = (IdxT)i;
-    local += key != 0;
-  }
-  atomicAdd(&s_count, local);
-  for (int size = 2; size <= cap_p2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncthreads();
-      for (int t = threadIdx.x; t < (cap_p2 >> 1); t += blockDim.x) {
-        const int i = 2 * t - (t & (stride - 1));
-        const int j = i + stride;
-        const uint32_t ki = k[i], kj = k[j];
-        const IdxT ii = ix[i], ij = ix[j];
-        const bool i_first = (ki > kj) || (ki == kj && ii < ij);
-        const bool want_i_first = ((i & size) == 0);
-        if (i_first != want_i_first) { k[i] = kj; k[j] = ki; ix[i] = ij; ix[j] = ii; }
-      }
-    }
-  }
-  __syncthreads();
-  const int nv = min(s_count, topn);
-  if (threadIdx.x == 0) nvalid[p] = nv;
-  for (int r = threadIdx.x; r < nv; r += blockDim.x) order[(size_t)p * cap + r] = (int)ix[r];
-}
-
-// global-memory fallback for more than 32768 candidates per problem (large images)
-__global__ void __launch_bounds__(1024) sort_desc_gmem_kernel(const float* __restrict__ keys, int cap, int cap_p2,
-                                                              const int* __restrict__ n_in, int topn,
-                                                              unsigned long long* __restrict__ tmp,
-                                                              int* __restrict__ order, int* __restrict__ nvalid) {
-  __shared__ int s_count;
-  const int p = blockIdx.x;
-  const int n = n_in ? min(n_in[p], cap) : cap;
-  unsigned long long* v = tmp + (size_t)p * cap_p2;
-  if (threadIdx.x == 0) s_count = 0;
-  __syncthreads();
-  int local = 0;
-  for (int i = threadIdx.x; i < cap_p2; i += blockDim.x) {
-    uint32_t key = 0;
-    if (i < n) key = score_key(keys[(size_t)p * cap + i]);
-    v[i] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
-    local += key != 0;
-  }
-  atomicAdd(&s_count, local);
-  for (int size = 2; size <= cap_p2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncthreads();
-      for (int t = threadIdx.x; t < (cap_p2 >> 1); t += blockDim.x) {
-        const int i = 2 * t - (t & (stride - 1));
-        const int j = i + stride;
-        const unsigned long long a = v[i], b = v[j];
-        const bool i_first = a > b;
-        const bool want_i_first = ((i & size) == 0);
-        if (i_first != want_i_first) { v[i] = b; v[j] = a; }
-      }
-    }
-  }
-  __syncthreads();
-  const int nv = min(s_count, topn);
-  if (threadIdx.x == 0) nvalid[p] = nv;
-  for (int r = threadIdx.x; r < nv; r += blockDim.x)
-    order[(size_t)p * cap + r] = (int)(0xFFFFFFFFu - (uint32_t)(v[r] & 0xFFFFFFFFull));
-}
 
 // ------------------------------------------------------------------ LSD radix sort (one CTA per problem)
 // Stable 4 x 8-bit passes over (key', index) pairs, key' = ~score_key: ascending key' == descending
@@ -179,15 +102,16 @@ __global__ void __launch_bounds__(1024) sort_desc_gmem_kernel(const float* __res
 // scatter) keep register use independent of the problem size; data ping-pongs through L2.
 template <int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const float* __restrict__ keys, int cap,
-                                                                     const int* __restrict__ n_in, int topn,
-                                                                     unsigned long long* __restrict__ tmp,
+                                                                     int n_all, const int* __restrict__ n_in,
+                                                                     int topn, unsigned long long* __restrict__ tmp,
                                                                      int* __restrict__ order,
                                                                      int* __restrict__ nvalid) {
+  constexpr int U = 4;                                   // rounds fetched ahead (independent loads in flight)
   __shared__ uint32_t hist[NWARPS][256];
   __shared__ uint32_t warp_tot[NWARPS];
   __shared__ int s_count;
   const int p = blockIdx.x;
-  const int n = n_in ? min(n_in[p], cap) : cap;
+  const int n = n_in ? min(n_in[p], n_all) : n_all;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   unsigned long long* bufA = tmp + (size_t)p * 2 * cap;
@@ -201,29 +125,33 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
     const int shift = pass * 8;
     const unsigned long long* src = (pass & 1) ? bufB : bufA;
     unsigned long long* dst = (pass & 1) ? bufA : bufB;
+    auto fetch = [&](int i) -> unsigned long long {       // (key', index) of item i of this pass' input
+      if (i >= hi) return 0ull;
+      if (pass == 0) {
+        const uint32_t k = score_key(keys[(size_t)p * cap + i]);
+        return ((unsigned long long)(~k) << 32) | (uint32_t)i;
+      }
+      return src[i];
+    };
     for (int d = lane; d < 256; d += 32) hist[warp][d] = 0;
     __syncwarp();
     // ---- sweep 1: per-warp digit counts
-    for (int base = lo; base < hi; base += 32) {
-      const int i = base + lane;
-      const bool act = i < hi;
-      unsigned long long v = 0;
-      if (act) {
-        if (pass == 0) {
-          const uint32_t k = score_key(keys[(size_t)p * cap + i]);
-          local_valid += k != 0;
-          v = ((unsigned long long)(~k) << 32) | (uint32_t)i;
-        } else {
-          v = src[i];
+    for (int base = lo; base < hi; base += 32 * U) {
+      unsigned long long v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = fetch(base + u * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool act = base + u * 32 + lane < hi;
+        if (pass == 0 && act) local_valid += (uint32_t)(v[u] >> 32) != 0xFFFFFFFFu;
+        const uint32_t digit = (uint32_t)(v[u] >> (32 + shift)) & 255u;
+        const uint32_t amask = __ballot_sync(0xffffffffu, act);
+        if (act) {
+          const uint32_t peers = __match_any_sync(amask, digit);
+          if ((peers & lt_mask) == 0) hist[warp][digit] += __popc(peers);    // leader of its digit group
         }
+        __syncwarp();
       }
-      const uint32_t digit = (uint32_t)(v >> (32 + shift)) & 255u;
-      const uint32_t amask = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        const uint32_t peers = __match_any_sync(amask, digit);
-        if ((peers & lt_mask) == 0) hist[warp][digit] += __popc(peers);      // leader of its digit group
-      }
-      __syncwarp();
     }
     __syncthreads();
     // ---- exclusive scan in digit-major order: entry j = d * NWARPS + w, 8 entries per thread
@@ -255,33 +183,29 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
     }
     __syncthreads();
     // ---- sweep 2: stable scatter
-    for (int base = lo; base < hi; base += 32) {
-      const int i = base + lane;
-      const bool act = i < hi;
-      unsigned long long v = 0;
-      if (act) {
-        if (pass == 0) {
-          const uint32_t k = score_key(keys[(size_t)p * cap + i]);
-          v = ((unsigned long long)(~k) << 32) | (uint32_t)i;
-        } else {
-          v = src[i];
+    for (int base = lo; base < hi; base += 32 * U) {
+      unsigned long long v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = fetch(base + u * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool act = base + u * 32 + lane < hi;
+        const uint32_t digit = (uint32_t)(v[u] >> (32 + shift)) & 255u;
+        const uint32_t amask = __ballot_sync(0xffffffffu, act);
+        if (act) {
+          const uint32_t peers = __match_any_sync(amask, digit);
+          const uint32_t old = hist[warp][digit];
+          const uint32_t pos = old + __popc(peers & lt_mask);
+          __syncwarp(amask);
+          if ((peers & lt_mask) == 0) hist[warp][digit] = old + __popc(peers);
+          if (pass < 3) {
+            dst[pos] = v[u];
+          } else if ((int)pos < topn && (uint32_t)(v[u] >> 32) != 0xFFFFFFFFu) {
+            order[(size_t)p * cap + pos] = (int)(uint32_t)v[u];                 // final pass: sorted indices
+          }
         }
+        __syncwarp();
       }
-      const uint32_t digit = (uint32_t)(v >> (32 + shift)) & 255u;
-      const uint32_t amask = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        const uint32_t peers = __match_any_sync(amask, digit);
-        const uint32_t old = hist[warp][digit];
-        const uint32_t pos = old + __popc(peers & lt_mask);
-        __syncwarp(amask);
-        if ((peers & lt_mask) == 0) hist[warp][digit] = old + __popc(peers);
-        if (pass < 3) {
-          dst[pos] = v;
-        } else if ((int)pos < topn && (uint32_t)(v >> 32) != 0xFFFFFFFFu) {
-          order[(size_t)p * cap + pos] = (int)(uint32_t)v;                    // final pass: sorted indices
-        }
-      }
-      __syncwarp();
     }
     __syncthreads();
   }
@@ -290,25 +214,28 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
   if (threadIdx.x == 0) nvalid[p] = min(s_count, topn);
 }
 
-static void run_sort(const float* keys, int problems, int cap, const int* n_in, int topn, int* order, int* nvalid,
-                     unsigned long long* tmp, cudaStream_t st) {
-  if (!problems || !cap) return;
-  LUMI_REQUIRE(tmp != nullptr, "sort: missing scratch");
-  if (cap > 4096) sort_desc_radix_kernel<32><<<problems, 1024, 0, st>>>(keys, cap, n_in, topn, tmp, order, nvalid);
-  else sort_desc_radix_kernel<8><<<problems, 256, 0, st>>>(keys, cap, n_in, topn, tmp, order, nvalid);
+// keys: [problems][cap]; the first n_all (<= cap) entries of each problem are sorted
+static void run_sort(const float* keys, int problems, int cap, int n_all, const int* n_in, int topn, int* order,
+                     int* nvalid, unsigned long long* tmp, cudaStream_t st) {
+  if (!problems || !cap || !n_all) return;
+  LUMI_REQUIRE(tmp != nullptr && n_all <= cap, "sort: missing scratch");
+  if (n_all > 4096)
+    sort_desc_radix_kernel<32><<<problems, 1024, 0, st>>>(keys, cap, n_all, n_in, topn, tmp, order, nvalid);
+  else
+    sort_desc_radix_kernel<8><<<problems, 256, 0, st>>>(keys, cap, n_all, n_in, topn, tmp, order, nvalid);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------ gather sorted
 __global__ void gather_sorted_kernel(const float* __restrict__ boxes, const float* __restrict__ keys,
-                                     const int* __restrict__ order, const int* __restrict__ nvalid, int cap,
+                                     const int* __restrict__ order, const int* __restrict__ nvalid, int cap, int ncap,
                                      float* __restrict__ sboxes, float* __restrict__ sscores) {
   const int p = blockIdx.y;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nvalid[p]) return;
   const size_t src = (size_t)p * cap + order[(size_t)p * cap + r];
-  const size_t dst = (size_t)p * cap + r;
+  const size_t dst = (size_t)p * ncap + r;
   reinterpret_cast<float4*>(sboxes)[dst] = reinterpret_cast<const float4*>(boxes)[src];
   sscores[dst] = keys[src];
 }
@@ -345,6 +272,8 @@ __device__ __forceinline__ bool iou_gt_norm(const NBox& a, const NBox& b, float 
 
 // grid (pair slot, problem); 64 threads; a block walks the upper-triangle (row block, col block) pairs
 // of its problem with a grid stride, so launch cost follows the live candidate count, not the capacity.
+// thr > 0 (every configuration in practice): branch-free inner loop -- the 2^-20 margin test decides
+// almost every pair, the IEEE divide only runs for ratios within the margin of the threshold.
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sboxes, const int* __restrict__ nvalid,
                                                       int cap, int words, float thr,
                                                       unsigned long long* __restrict__ mask) {
@@ -352,33 +281,63 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   const int n = nvalid[p];
   const int nw = (n + 63) >> 6;
   const long npairs = (long)nw * (nw + 1) / 2;
-  __shared__ float4 cbox[64];
-  __shared__ NBox cnorm[64];
+  __shared__ float4 cbox[64];        // raw boxes (generic path)
+  __shared__ float4 cmm[64];         // (xmin, ymin, xmax, ymax)
+  __shared__ float carea[64];        // area, or -1 for columns past the end
   const float4* B = reinterpret_cast<const float4*>(sboxes) + (size_t)p * cap;
   const int t = threadIdx.x;
-  for (long pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
-    // pair index -> (rb, cb >= rb); row rb starts at rb*(2nw-rb+1)/2
+  // pair index -> (rb, cb >= rb): row rb starts at rb*(2nw-rb+1)/2; decoded once, then advanced incrementally
+  long pr = blockIdx.x;
+  int rb = 0;
+  if (pr < npairs) {
     const double disc = (2.0 * nw + 1.0) * (2.0 * nw + 1.0) - 8.0 * (double)pr;
-    int rb = (int)(((2.0 * nw + 1.0) - sqrt(disc)) * 0.5);
+    rb = (int)(((2.0 * nw + 1.0) - sqrt(disc)) * 0.5);
     if (rb < 0) rb = 0;
     if (rb > nw - 1) rb = nw - 1;
     while ((long)rb * (2 * nw - rb + 1) / 2 > pr) --rb;
     while ((long)(rb + 1) * (2 * nw - rb) / 2 <= pr) ++rb;
+  }
+  for (; pr < npairs; pr += gridDim.x) {
+    while ((long)(rb + 1) * (2 * nw - rb) / 2 <= pr) ++rb;
     const int cb = rb + (int)(pr - (long)rb * (2 * nw - rb + 1) / 2);
     __syncthreads();
-    if (cb * 64 + t < n) { cbox[t] = B[cb * 64 + t]; cnorm[t] = normalise_box(cbox[t]); }
+    {
+      const bool in = cb * 64 + t < n;
+      const float4 c = in ? B[cb * 64 + t] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const NBox nb = normalise_box(c);
+      cbox[t] = c;
+      cmm[t] = make_float4(nb.xmin, nb.ymin, nb.xmax, nb.ymax);
+      carea[t] = in ? nb.area : -1.f;
+    }
     __syncthreads();
     const int i = rb * 64 + t;
     if (i >= n) continue;
     const float4 bi = B[i];
     unsigned long long bits = 0ull;
-    const int jmax = min(64, n - cb * 64);
-    if (thr >= 0.f) {
+    if (thr > 0.f) {
       const NBox ni = normalise_box(bi);
-      const int j0 = (cb == rb) ? t + 1 : 0;           // only columns > i
-      for (int j = j0; j < jmax; ++j)
-        if (iou_gt_norm(ni, cnorm[j], thr)) bits |= 1ull << j;
-    } else {                                            // negative thresholds: generic (exact) path
+      const bool row_ok = ni.area > 0.f;
+      uint32_t lo = 0u, hi = 0u;
+#pragma unroll 8
+      for (int j = 0; j < 64; ++j) {
+        const float4 c = cmm[j];
+        const float ca = carea[j];
+        const float dx = __fsub_rn(fminf(ni.xmax, c.z), fmaxf(ni.xmin, c.x));
+        const float dy = __fsub_rn(fminf(ni.ymax, c.w), fmaxf(ni.ymin, c.y));
+        const float inter = __fmul_rn(fmaxf(dy, 0.f), fmaxf(dx, 0.f));
+        const float uni = __fsub_rn(__fadd_rn(ni.area, ca), inter);
+        const float tt = __fmul_rn(thr, uni);
+        const bool ok = row_ok && ca > 0.f && inter > 0.f;
+        const bool sane = uni > 1e-30f && uni < 1e30f && inter < 1e30f;
+        bool pred = ok && sane && inter > __fmul_rn(tt, 1.00000095f);
+        const bool amb = ok && !pred && !(sane && inter < __fmul_rn(tt, 0.99999905f));
+        if (amb) pred = __fdiv_rn(inter, uni) > thr;          // rare: ratio within 2^-20 of the threshold
+        if (j < 32) lo |= (uint32_t)pred << j; else hi |= (uint32_t)pred << (j - 32);
+      }
+      bits = ((unsigned long long)hi << 32) | lo;
+      if (cb == rb) bits &= ~((2ull << t) - 1ull);            // only columns > i
+    } else {                                                  // thr <= 0: generic exact path
+      const int jmax = min(64, n - cb * 64);
       for (int j = 0; j < jmax; ++j) {
         const int col = cb * 64 + j;
         if (col > i && iou_gt(bi, cbox[j], thr)) bits |= 1ull << j;
@@ -543,7 +502,7 @@ static void run_nms(NmsWorkspace& ws, int problems, float thr, int max_out, cuda
   if (!problems) return;
   long maxpairs = (long)ws.words * (ws.words + 1) / 2;
   dim3 grid((unsigned)(maxpairs < 2048 ? maxpairs : 2048), problems);
-  nms_mask_kernel<<<grid, 64, 0, st>>>(ws.sboxes, ws.nvalid, ws.cap, ws.words, thr, ws.mask);
+  nms_mask_kernel<<<grid, 64, 0, st>>>(ws.sboxes, ws.nvalid, ws.ncap, ws.words, thr, ws.mask);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
   const size_t staged_smem = ((size_t)ws.words + 2 * 64 * (size_t)ws.words) * sizeof(unsigned long long);
@@ -554,11 +513,11 @@ static void run_nms(NmsWorkspace& ws, int problems, float thr, int max_out, cuda
                                            200 * 1024));
       attr = true;
     }
-    nms_scan_staged_kernel<<<problems, 256, staged_smem, st>>>(ws.mask, ws.nvalid, ws.cap, ws.words, max_out, ws.keep,
+    nms_scan_staged_kernel<<<problems, 256, staged_smem, st>>>(ws.mask, ws.nvalid, ws.ncap, ws.words, max_out, ws.keep,
                                                               ws.nkeep);
   } else {
     size_t smem = (size_t)ws.words * sizeof(unsigned long long);
-    nms_scan_kernel<<<problems, 256, smem, st>>>(ws.mask, ws.nvalid, ws.cap, ws.words, max_out, ws.keep, ws.nkeep);
+    nms_scan_kernel<<<problems, 256, smem, st>>>(ws.mask, ws.nvalid, ws.ncap, ws.words, max_out, ws.keep, ws.nkeep);
   }
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
@@ -629,16 +588,18 @@ void launch_rpn_proposals(const float* cls, const float* box, long img_stride_cl
     LUMI_CUDA_CHECK(cudaMemset2DAsync(ws.keys + p.na, (size_t)ws.cap * sizeof(float), 0xFF,
                                       (size_t)(ws.cap - p.na) * sizeof(float), nimg, st));   // 0xFFFFFFFF = NaN -> invalid
   }
-  run_sort(ws.keys, nimg, ws.cap, nullptr, p.pre_nms_top_n, ws.order, ws.nvalid, ws.sort_tmp, st);
-  dim3 g2(cdiv(ws.cap, 256), nimg);
-  gather_sorted_kernel<<<g2, 256, 0, st>>>(ws.boxes, ws.keys, ws.order, ws.nvalid, ws.cap, ws.sboxes, ws.sscores);
+  run_sort(ws.keys, nimg, ws.cap, p.na, nullptr, p.pre_nms_top_n, ws.order, ws.nvalid, ws.sort_tmp, st);
+  LUMI_REQUIRE(p.pre_nms_top_n <= ws.ncap || p.na <= ws.ncap, "rpn_proposals: NMS workspace smaller than pre_nms_top_n");
+  dim3 g2(cdiv(ws.ncap, 256), nimg);
+  gather_sorted_kernel<<<g2, 256, 0, st>>>(ws.boxes, ws.keys, ws.order, ws.nvalid, ws.cap, ws.ncap, ws.sboxes,
+                                           ws.sscores);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
   const float thr = p.apply_nms ? p.nms_threshold : INFINITY;
   LUMI_REQUIRE(p.post_nms_top_n <= ws.max_out, "rpn_proposals: post_nms_top_n exceeds workspace");
   run_nms(ws, nimg, thr, p.post_nms_top_n, st);
   dim3 g3(cdiv(p.post_nms_top_n, 256), nimg);
-  rpn_output_kernel<<<g3, 256, 0, st>>>(ws.sboxes, ws.sscores, ws.keep, ws.nkeep, ws.cap, p.post_nms_top_n,
+  rpn_output_kernel<<<g3, 256, 0, st>>>(ws.sboxes, ws.sscores, ws.keep, ws.nkeep, ws.ncap, p.post_nms_top_n,
                                         p.clip_after_nms, p.im_h, p.im_w, proposals, scores, counts);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
@@ -728,9 +689,10 @@ void launch_class_detections(const float* boxes_in, long boxes_img_stride, const
   if (p.r < ws.cap)
     LUMI_CUDA_CHECK(cudaMemset2DAsync(ws.keys + p.r, (size_t)ws.cap * sizeof(float), 0xFF,
                                       (size_t)(ws.cap - p.r) * sizeof(float), P, st));
-  run_sort(ws.keys, P, ws.cap, nullptr, ws.cap, ws.order, ws.nvalid, ws.sort_tmp, st);
-  dim3 g2(cdiv(ws.cap, 256), P);
-  gather_sorted_kernel<<<g2, 256, 0, st>>>(ws.boxes, ws.keys, ws.order, ws.nvalid, ws.cap, ws.sboxes, ws.sscores);
+  run_sort(ws.keys, P, ws.cap, p.r, nullptr, ws.cap, ws.order, ws.nvalid, ws.sort_tmp, st);
+  dim3 g2(cdiv(ws.ncap, 256), P);
+  gather_sorted_kernel<<<g2, 256, 0, st>>>(ws.boxes, ws.keys, ws.order, ws.nvalid, ws.cap, ws.ncap, ws.sboxes,
+                                           ws.sscores);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
   run_nms(ws, P, p.nms_threshold, p.class_max, st);
@@ -741,12 +703,12 @@ void launch_class_detections(const float* boxes_in, long boxes_img_stride, const
   unsigned long long* fscratch = reinterpret_cast<unsigned long long*>(
       (reinterpret_cast<uintptr_t>(fnvalid + nimg) + 15) & ~(uintptr_t)15);
   dim3 g3(cdiv(p.class_max, 128), P);
-  det_concat_kernel<<<g3, 128, 0, st>>>(ws.sscores, ws.keep, ws.nkeep, p.nc, ws.cap, p.class_max, fkeys);
+  det_concat_kernel<<<g3, 128, 0, st>>>(ws.sscores, ws.keep, ws.nkeep, p.nc, ws.ncap, p.class_max, fkeys);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
-  run_sort(fkeys, nimg, fcap, nullptr, p.total_max, forder, fnvalid, fscratch, st);
+  run_sort(fkeys, nimg, fcap, fcap, nullptr, p.total_max, forder, fnvalid, fscratch, st);
   dim3 g4(cdiv(p.total_max, 128), nimg);
-  det_output_kernel<<<g4, 128, 0, st>>>(ws.sboxes, ws.sscores, ws.keep, forder, fnvalid, p.nc, ws.cap, p.class_max,
+  det_output_kernel<<<g4, 128, 0, st>>>(ws.sboxes, ws.sscores, ws.keep, forder, fnvalid, p.nc, ws.ncap, p.class_max,
                                         p.total_max, objects, labels, probs, counts);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
@@ -757,7 +719,7 @@ void launch_sort_desc(const float* scores, int n, int* idx_out, NmsWorkspace& ws
   LUMI_REQUIRE(n <= ws.cap && ws.problems >= 1, "sort_desc: workspace too small");
   LUMI_CUDA_CHECK(cudaMemsetAsync(ws.keys, 0xFF, (size_t)ws.cap * sizeof(float), st));
   LUMI_CUDA_CHECK(cudaMemcpyAsync(ws.keys, scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  run_sort(ws.keys, 1, ws.cap, nullptr, ws.cap, ws.order, ws.nvalid, ws.sort_tmp, st);
+  run_sort(ws.keys, 1, ws.cap, n, nullptr, ws.cap, ws.order, ws.nvalid, ws.sort_tmp, st);
   LUMI_CUDA_CHECK(cudaMemcpyAsync(idx_out, ws.order, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
 }
 
@@ -765,7 +727,7 @@ __global__ void set_int_kernel(int* p, int v) { *p = v; }
 
 void launch_nms_sorted(const float* boxes_sorted, int n, float thr, int max_out, NmsWorkspace& ws, int* keep,
                        int* nkeep, cudaStream_t st) {
-  LUMI_REQUIRE(n <= ws.cap && max_out <= ws.max_out, "nms_sorted: workspace too small");
+  LUMI_REQUIRE(n <= ws.ncap && max_out <= ws.max_out, "nms_sorted: workspace too small");
   LUMI_CUDA_CHECK(cudaMemcpyAsync(ws.sboxes, boxes_sorted, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   set_int_kernel<<<1, 1, 0, st>>>(ws.nvalid, n);
   count_launch();

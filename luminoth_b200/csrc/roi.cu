@@ -59,8 +59,8 @@ __device__ __forceinline__ void row_interp(const float* f, size_t rowbase, int c
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    h0[j] = __fadd_rn(l0[j], __fmul_rn(__fsub_rn(r0[j], l0[j]), s0.lerp));
-    h1[j] = __fadd_rn(l1[j], __fmul_rn(__fsub_rn(r1[j], l1[j]), s1.lerp));
+    h0[j] = fmaf(r0[j] - l0[j], s0.lerp, l0[j]);      // top + (right - left) * lerp, one rounding fewer than TF
+    h1[j] = fmaf(r1[j] - l1[j], s1.lerp, l1[j]);
   }
 }
 
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256, 2) roi_pool_kernel(const RoiArgs a) {
         const bool ok = y0.ok && (sx ? x1.ok : x0.ok);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float v = ok ? __fadd_rn(t0[sx][j], __fmul_rn(__fsub_rn(b0[sx][j], t0[sx][j]), y0.lerp)) : 0.f;
+          const float v = ok ? fmaf(b0[sx][j] - t0[sx][j], y0.lerp, t0[sx][j]) : 0.f;
           best[j] = fmaxf(best[j], v);              // extrapolation_value = 0
         }
       }
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256, 2) roi_pool_kernel(const RoiArgs a) {
         const bool ok = y1.ok && (sx ? x1.ok : x0.ok);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float v = ok ? __fadd_rn(t1[sx][j], __fmul_rn(__fsub_rn(b1[sx][j], t1[sx][j]), y1.lerp)) : 0.f;
+          const float v = ok ? fmaf(b1[sx][j] - t1[sx][j], y1.lerp, t1[sx][j]) : 0.f;
           best[j] = fmaxf(best[j], v);
         }
       }
