@@ -199,6 +199,7 @@ void launch_conv_simt(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
 struct TcArgs {
   CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
   CUtensorMap tm_o_hi, tm_o_lo;    // output planes, box {32 ch, tw, th, nb}, SWIZZLE_64B (split outputs only)
+  CUtensorMap tm_r_hi, tm_r_lo;    // residual planes, box {32 ch, tw*rs, th*rs, nb} with traversal stride rs (RES kernels)
   const float* scale; const float* bias;
   __half* out_hi; __half* out_lo; float* out_f32;
   const __half* res_hi; const __half* res_lo;
@@ -222,12 +223,15 @@ constexpr int TC_A_BYTES = 128 * 128;       // 128 pixel rows x 64 fp16 (one 128
 // K loop (their truncation error is 2^-11 times smaller still).
 constexpr int TC_CHUNK_STAGES = 4;          // 16 hi*hi MMAs per D1 chunk
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool RES = false>
 struct TcCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
   static constexpr int OUT_STAGE_BYTES = 2 * 2 * 128 * 64;   // per column half: hi + lo slabs of 128 rows x 32 ch
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // RES: the whole residual tile (BN/32 slabs x {hi, lo} x 128 rows x 64 B) is TMA-prefetched at tile start
+  static constexpr int RES_STAGE_BYTES = RES ? (BN / 32) * 2 * 128 * 64 : 0;
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + OUT_STAGE_BYTES + RES_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 4 * BN;          // D1[0], D1[1], D2[0], D2[1]  (256 or 512 columns)
 };
 
@@ -238,18 +242,21 @@ constexpr int TC_THREADS = 320;                     // warp 0 TMA, warp 1 MMA, w
 // free-running stage / chunk counters, so the producer prefetches the next tile's operands and the
 // tensor core starts the next tile while the epilogue warps are still storing the previous one
 // (D1 and D2 are double-buffered in TMEM).
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
-  using Cfg = TcCfg<BN, STAGES>;
+  using Cfg = TcCfg<BN, STAGES, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES;      // [2 halves][hi, lo][128 rows x 64 B], 64 B swizzle
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + Cfg::OUT_STAGE_BYTES);
+  uint8_t* res_stage = out_stage + Cfg::OUT_STAGE_BYTES;      // [BN/32 slabs][hi, lo][128 rows x 64 B] (RES only)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_stage + Cfg::RES_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full_bar = empty_bar + STAGES;       // [2]  D1[buf] chunk complete (tcgen05.commit)
   uint64_t* acc_empty_bar = acc_full_bar + 2;        // [2]  D1[buf] drained by the 8 epilogue warps
   uint64_t* d2_empty_bar = acc_empty_bar + 2;        // [2]  D2[tbuf] drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty_bar + 2);
+  uint64_t* res_full_bar = d2_empty_bar + 2;         // residual tile landed (TMA)
+  uint64_t* res_empty_bar = res_full_bar + 1;        // residual tile consumed by the 8 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
@@ -261,12 +268,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full_bar[s], 1); mbar_init(&acc_empty_bar[s], 8); mbar_init(&d2_empty_bar[s], 8);
     }
+    mbar_init(res_full_bar, 1); mbar_init(res_empty_bar, 8);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tm_a_hi); tma_prefetch_desc(&a.tm_a_lo);
     tma_prefetch_desc(&a.tm_b_hi); tma_prefetch_desc(&a.tm_b_lo);
     if (!a.out_f32) { tma_prefetch_desc(&a.tm_o_hi); tma_prefetch_desc(&a.tm_o_lo); }
+    if (RES) { tma_prefetch_desc(&a.tm_r_hi); tma_prefetch_desc(&a.tm_r_lo); }
   }
   if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
@@ -282,11 +291,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       // ---------------- TMA producer: one (tap, 64-channel) slice per stage
       const uint32_t stage_tx = 2u * (uint32_t)rows_valid * 128u + 2u * (uint32_t)Cfg::B_BYTES;
-      uint32_t git = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      uint32_t git = 0, tile_iter = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
         const int nt = t % a.n_tiles, mt = t / a.n_tiles;
         const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
         const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
+        if (RES) {        // residual tile of THIS tile: needed only by its epilogue, so it streams in under the K loop
+          mbar_wait(res_empty_bar, (tile_iter & 1u) ^ 1u);
+          mbar_arrive_expect_tx(res_full_bar, (uint32_t)(BN / 32) * 2u * (uint32_t)rows_valid * 64u);
+#pragma unroll
+          for (int sl = 0; sl < BN / 32; ++sl) {
+            tma_load_4d(res_stage + (sl * 2 + 0) * 8192, &a.tm_r_hi, res_full_bar, n0 + sl * 32, x0 * a.res_stride,
+                        y0 * a.res_stride, img0);
+            tma_load_4d(res_stage + (sl * 2 + 1) * 8192, &a.tm_r_lo, res_full_bar, n0 + sl * 32, x0 * a.res_stride,
+                        y0 * a.res_stride, img0);
+          }
+        }
         for (int tap = 0; tap < a.kh * a.kw; ++tap) {
           const int r = tap / a.kw, s = tap % a.kw;
           const int iy = y0 * a.stride + r * a.rate - a.pad_t, ix = x0 * a.stride + s * a.rate - a.pad_l;
@@ -434,7 +454,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             v[g * 4 + 2] = fmaf(racc[ch * 32 + g * 4 + 2], sc.z, bi.z);
             v[g * 4 + 3] = fmaf(racc[ch * 32 + g * 4 + 3], sc.w, bi.w);
           }
-          if (a.res_hi && valid) {     // residual tensors always have cout % 32 == 0 channels
+          if (RES) {                   // residual slab was TMA-prefetched into shared memory (64 B swizzle)
+            if (ch == 0) mbar_wait(res_full_bar, tile_iter & 1u);
+            const int sl = half * (HC / 32) + ch;
+            const int rsw = (row >> 1) & 3;
+            const uint8_t* rh = res_stage + (sl * 2 + 0) * 8192 + row * 64;
+            const uint8_t* rl = res_stage + (sl * 2 + 1) * 8192 + row * 64;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 h4 = *reinterpret_cast<const uint4*>(rh + ((g ^ rsw) << 4));
+              const uint4 l4 = *reinterpret_cast<const uint4*>(rl + ((g ^ rsw) << 4));
+              const __half* ph = reinterpret_cast<const __half*>(&h4);
+              const __half* pl = reinterpret_cast<const __half*>(&l4);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] += join_f16(ph[j], pl[j]);
+            }
+            if (ch == HC / 32 - 1) {   // this warp is done with the residual tile
+              __syncwarp();
+              if (lane == 0) mbar_arrive(res_empty_bar);
+            }
+          } else if (a.res_hi && valid) {     // residual tensors always have cout % 32 == 0 channels
             const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + rpix * a.cout + c0);
             const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + rpix * a.cout + c0);
 #pragma unroll
@@ -538,13 +577,14 @@ static CUtensorMap make_map_act(const __half* base, int n, int h, int w, int c, 
   return m;
 }
 
-// output plane: box {32 ch, tw, th, nb}, 64 B swizzle (matches the epilogue's staging layout)
-static CUtensorMap make_map_out(const __half* base, int n, int h, int w, int c, int nb, int th, int tw) {
+// output / residual plane: box {32 ch, tw, th, nb} (x traversal stride rs for subsampled residuals),
+// 64 B swizzle (matches the epilogue's staging layout)
+static CUtensorMap make_map_out(const __half* base, int n, int h, int w, int c, int nb, int th, int tw, int rs = 1) {
   CUtensorMap m;
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  cuuint32_t box[4] = {32, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {32, (cuuint32_t)(tw * rs), (cuuint32_t)(th * rs), (cuuint32_t)nb};
+  cuuint32_t es[4] = {1, (cuuint32_t)rs, (cuuint32_t)rs, 1};
   CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -586,12 +626,12 @@ static CUtensorMap cached_act_map(const __half* base, int n, int h, int w, int c
   g_map_cache[k] = m;
   return m;
 }
-static CUtensorMap cached_out_map(const __half* base, int n, int h, int w, int c, int nb, int th, int tw) {
+static CUtensorMap cached_out_map(const __half* base, int n, int h, int w, int c, int nb, int th, int tw, int rs = 1) {
   std::lock_guard<std::mutex> lk(g_map_mutex);
-  MapKey k{base, n, h, w, -c, nb, th, tw};                 // negative c: output-map key space
+  MapKey k{base, n, h, w, -c, nb, th * 16 + rs, tw};       // negative c: output-map key space
   auto it = g_map_cache.find(k);
   if (it != g_map_cache.end()) return it->second;
-  CUtensorMap m = make_map_out(base, n, h, w, c, nb, th, tw);
+  CUtensorMap m = make_map_out(base, n, h, w, c, nb, th, tw, rs);
   g_map_cache[k] = m;
   return m;
 }
@@ -643,18 +683,18 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool RES>
 static void launch_tc_cfg(const TcArgs& a, cudaStream_t st) {
-  using Cfg = TcCfg<BN, STAGES>;
+  using Cfg = TcCfg<BN, STAGES, RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    LUMI_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LUMI_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const long total = (long)a.tiles_w * a.tiles_h * a.tiles_n * a.n_tiles;
   const int grid = (int)(total < sm_count() ? total : sm_count());     // persistent: one CTA per SM
-  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  conv_tc_kernel<BN, STAGES, RES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
@@ -689,8 +729,16 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   a.n_tiles = L.cout_pad / bn;
   a.stride = L.stride;
   a.overflow = io.overflow_flag;
-  if (bn == 128) launch_tc_cfg<128, 3>(a, st);
-  else launch_tc_cfg<64, 4>(a, st);
+  const bool res_tma = io.res.hi != nullptr && bn == 128 && !io.out_f32;
+  if (res_tma) {          // residual tile prefetched by TMA (box over the unit's input, subsampled by res_stride)
+    a.tm_r_hi = cached_out_map(io.res.hi, io.res.n, io.res.h, io.res.w, io.res.c, nb, th, tw, io.res_stride);
+    a.tm_r_lo = cached_out_map(io.res.lo, io.res.n, io.res.h, io.res.w, io.res.c, nb, th, tw, io.res_stride);
+    launch_tc_cfg<128, 2, true>(a, st);
+  } else if (bn == 128) {
+    launch_tc_cfg<128, 3, false>(a, st);
+  } else {
+    launch_tc_cfg<64, 4, false>(a, st);
+  }
 }
 
 // ---------------------------------------------------------------- host: weight packing

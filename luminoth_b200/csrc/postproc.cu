@@ -94,12 +94,13 @@ void nms_workspace_free(NmsWorkspace& ws) {
 __device__ __forceinline__ uint32_t score_key(float s) { return (s >= 0.f) ? (__float_as_uint(s) + 1u) : 0u; }
 
 // ------------------------------------------------------------------ LSD radix sort (one CTA per problem)
-// Stable 4 x 8-bit passes over (key', index) pairs, key' = ~score_key: ascending key' == descending
+// Stable 8 x 4-bit passes over (key', index) pairs, key' = ~score_key: ascending key' == descending
 // score, stability == "ties -> lower index first" (tf.nn.top_k / NMS candidate order).  Each warp owns a
-// contiguous segment and walks it 32 items at a time; __match_any_sync gives the rank among equal
-// digits inside the round, a per-warp digit table in shared memory the rank across rounds, and one
-// block-wide exclusive scan in digit-major order the global offsets.  Two sweeps per pass (count, then
-// scatter) keep register use independent of the problem size; data ping-pongs through L2.
+// contiguous segment and walks it 32 items at a time; 16 ballots give every lane the mask of its digit
+// group (rank inside the round = popc below the lane; __match_any_sync is ~10x slower here), a per-warp
+// digit table in shared memory carries the rank across rounds, and one block-wide exclusive scan in
+// digit-major order yields the global offsets.  Two sweeps per pass (count, then scatter) keep register
+// use independent of the problem size; data ping-pongs through L2.
 template <int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const float* __restrict__ keys, int cap,
                                                                      int n_all, const int* __restrict__ n_in,
@@ -107,7 +108,8 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
                                                                      int* __restrict__ order,
                                                                      int* __restrict__ nvalid) {
   constexpr int U = 4;                                   // rounds fetched ahead (independent loads in flight)
-  __shared__ uint32_t hist[NWARPS][256];
+  constexpr int BITS = 4, BINS = 16, PASSES = 32 / BITS;
+  __shared__ uint32_t hist[NWARPS][BINS];
   __shared__ uint32_t warp_tot[NWARPS];
   __shared__ int s_count;
   const int p = blockIdx.x;
@@ -121,8 +123,18 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
   int local_valid = 0;
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = pass * 8;
+  // mask of the lanes (among the active ones) that hold the same digit as this lane
+  auto group_mask = [&](uint32_t digit, bool act) -> uint32_t {
+    uint32_t mine = 0u;
+#pragma unroll
+    for (int d = 0; d < BINS; ++d) {
+      const uint32_t b = __ballot_sync(0xffffffffu, act && digit == (uint32_t)d);
+      if (digit == (uint32_t)d) mine = b;
+    }
+    return mine;
+  };
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const int shift = pass * BITS;
     const unsigned long long* src = (pass & 1) ? bufB : bufA;
     unsigned long long* dst = (pass & 1) ? bufA : bufB;
     auto fetch = [&](int i) -> unsigned long long {       // (key', index) of item i of this pass' input
@@ -133,7 +145,7 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
       }
       return src[i];
     };
-    for (int d = lane; d < 256; d += 32) hist[warp][d] = 0;
+    if (lane < BINS) hist[warp][lane] = 0;
     __syncwarp();
     // ---- sweep 1: per-warp digit counts
     for (int base = lo; base < hi; base += 32 * U) {
@@ -144,26 +156,19 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
       for (int u = 0; u < U; ++u) {
         const bool act = base + u * 32 + lane < hi;
         if (pass == 0 && act) local_valid += (uint32_t)(v[u] >> 32) != 0xFFFFFFFFu;
-        const uint32_t digit = (uint32_t)(v[u] >> (32 + shift)) & 255u;
-        const uint32_t amask = __ballot_sync(0xffffffffu, act);
-        if (act) {
-          const uint32_t peers = __match_any_sync(amask, digit);
-          if ((peers & lt_mask) == 0) hist[warp][digit] += __popc(peers);    // leader of its digit group
-        }
+        const uint32_t digit = (uint32_t)(v[u] >> (32 + shift)) & (BINS - 1);
+        const uint32_t peers = group_mask(digit, act);
+        if (act && (peers & lt_mask) == 0) hist[warp][digit] += __popc(peers);   // leader of its digit group
         __syncwarp();
       }
     }
     __syncthreads();
-    // ---- exclusive scan in digit-major order: entry j = d * NWARPS + w, 8 entries per thread
+    // ---- exclusive scan in digit-major order: entry j = d * NWARPS + w  (BINS * NWARPS <= blockDim entries)
     {
-      uint32_t v[8], sum = 0;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int j = threadIdx.x * 8 + e;
-        v[e] = hist[j % NWARPS][j / NWARPS];
-        sum += v[e];
-      }
-      uint32_t incl = sum;
+      const int j = threadIdx.x;
+      const bool has = j < BINS * NWARPS;
+      const uint32_t val = has ? hist[j % NWARPS][j / NWARPS] : 0u;
+      uint32_t incl = val;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -173,13 +178,7 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
       __syncthreads();
       uint32_t wbase = 0;
       for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
-      uint32_t run = wbase + incl - sum;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int j = threadIdx.x * 8 + e;
-        hist[j % NWARPS][j / NWARPS] = run;
-        run += v[e];
-      }
+      if (has) hist[j % NWARPS][j / NWARPS] = wbase + incl - val;
     }
     __syncthreads();
     // ---- sweep 2: stable scatter
@@ -190,15 +189,14 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const bool act = base + u * 32 + lane < hi;
-        const uint32_t digit = (uint32_t)(v[u] >> (32 + shift)) & 255u;
-        const uint32_t amask = __ballot_sync(0xffffffffu, act);
+        const uint32_t digit = (uint32_t)(v[u] >> (32 + shift)) & (BINS - 1);
+        const uint32_t peers = group_mask(digit, act);
         if (act) {
-          const uint32_t peers = __match_any_sync(amask, digit);
           const uint32_t old = hist[warp][digit];
           const uint32_t pos = old + __popc(peers & lt_mask);
-          __syncwarp(amask);
+          __syncwarp(__activemask());
           if ((peers & lt_mask) == 0) hist[warp][digit] = old + __popc(peers);
-          if (pass < 3) {
+          if (pass < PASSES - 1) {
             dst[pos] = v[u];
           } else if ((int)pos < topn && (uint32_t)(v[u] >> 32) != 0xFFFFFFFFu) {
             order[(size_t)p * cap + pos] = (int)(uint32_t)v[u];                 // final pass: sorted indices
@@ -270,6 +268,10 @@ __device__ __forceinline__ bool iou_gt_norm(const NBox& a, const NBox& b, float 
   return __fdiv_rn(inter, uni) > thr;
 }
 
+__device__ __noinline__ bool iou_exact_gt(float inter, float uni, float thr) {
+  return __fdiv_rn(inter, uni) > thr;                          // inter > 0, uni finite here; NaN/inf compare false
+}
+
 // grid (pair slot, problem); 64 threads; a block walks the upper-triangle (row block, col block) pairs
 // of its problem with a grid stride, so launch cost follows the live candidate count, not the capacity.
 // thr > 0 (every configuration in practice): branch-free inner loop -- the 2^-20 margin test decides
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
       const NBox nb = normalise_box(c);
       cbox[t] = c;
       cmm[t] = make_float4(nb.xmin, nb.ymin, nb.xmax, nb.ymax);
-      carea[t] = in ? nb.area : -1.f;
+      carea[t] = (in && nb.area > 0.f) ? nb.area : INFINITY;   // inf union -> never > thr (matches iou == 0)
     }
     __syncthreads();
     const int i = rb * 64 + t;
@@ -316,23 +318,21 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
     unsigned long long bits = 0ull;
     if (thr > 0.f) {
       const NBox ni = normalise_box(bi);
-      const bool row_ok = ni.area > 0.f;
       uint32_t lo = 0u, hi = 0u;
-#pragma unroll 8
-      for (int j = 0; j < 64; ++j) {
-        const float4 c = cmm[j];
-        const float ca = carea[j];
-        const float dx = __fsub_rn(fminf(ni.xmax, c.z), fmaxf(ni.xmin, c.x));
-        const float dy = __fsub_rn(fminf(ni.ymax, c.w), fmaxf(ni.ymin, c.y));
-        const float inter = __fmul_rn(fmaxf(dy, 0.f), fmaxf(dx, 0.f));
-        const float uni = __fsub_rn(__fadd_rn(ni.area, ca), inter);
-        const float tt = __fmul_rn(thr, uni);
-        const bool ok = row_ok && ca > 0.f && inter > 0.f;
-        const bool sane = uni > 1e-30f && uni < 1e30f && inter < 1e30f;
-        bool pred = ok && sane && inter > __fmul_rn(tt, 1.00000095f);
-        const bool amb = ok && !pred && !(sane && inter < __fmul_rn(tt, 0.99999905f));
-        if (amb) pred = __fdiv_rn(inter, uni) > thr;          // rare: ratio within 2^-20 of the threshold
-        if (j < 32) lo |= (uint32_t)pred << j; else hi |= (uint32_t)pred << (j - 32);
+      if (ni.area > 0.f) {
+        const float thr_hi = __fmul_rn(thr, 1.00000095f), thr_lo = __fmul_rn(thr, 0.99999905f);
+#pragma unroll 16
+        for (int j = 0; j < 64; ++j) {
+          const float4 c = cmm[j];
+          const float ca = carea[j];                           // +inf for columns that can never suppress
+          const float dx = __fsub_rn(fminf(ni.xmax, c.z), fmaxf(ni.xmin, c.x));
+          const float dy = __fsub_rn(fminf(ni.ymax, c.w), fmaxf(ni.ymin, c.y));
+          const float inter = __fmul_rn(fmaxf(dy, 0.f), fmaxf(dx, 0.f));
+          const float uni = __fsub_rn(__fadd_rn(ni.area, ca), inter);
+          bool pred = inter > __fmul_rn(thr_hi, uni);          // ratio > thr (1 + 2^-21): certainly suppressed
+          if (!pred && inter >= __fmul_rn(thr_lo, uni)) pred = iou_exact_gt(inter, uni, thr);   // within the margin
+          if (j < 32) lo |= (uint32_t)pred << j; else hi |= (uint32_t)pred << (j - 32);
+        }
       }
       bits = ((unsigned long long)hi << 32) | lo;
       if (cb == rb) bits &= ~((2ull << t) - 1ull);            // only columns > i
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long*
   if (threadIdx.x == 0) nkeep[p] = s_total;
 }
 
-// Staged variant: the mask rows of chunk c+1 (only the words >= c+1, the upper triangle) are bulk-copied
+// Staged variant: the 64 mask rows of chunk c+1 (one contiguous block) are bulk-copied
 // (cp.async.bulk -> mbarrier) into shared memory while chunk c is resolved, so the greedy walk never
 // waits on an L2 round trip: diag resolve and the OR of the kept rows both read shared memory.
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -434,7 +434,6 @@ __global__ void __launch_bounds__(256) nms_scan_staged_kernel(const unsigned lon
   const int p = blockIdx.x;
   const int n = nvalid[p];
   const int nw = (n + 63) >> 6;
-  const int nw_e = (nw + 1) & ~1;                             // 16 B granularity of the bulk copies
   const unsigned long long* M = mask + (size_t)p * cap * words;
   for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = 0ull;
   if (threadIdx.x == 0) {
@@ -443,14 +442,13 @@ __global__ void __launch_bounds__(256) nms_scan_staged_kernel(const unsigned lon
     fence_mbar_init();
   }
   __syncthreads();
-  auto issue = [&](int c) {             // rows of chunk c, words [c_e, nw_e) -> buf[c & 1]; threads 0..63
-    const int c_e = c & ~1;
+  auto issue = [&](int c) {             // rows of chunk c are contiguous in the mask: one bulk copy -> buf[c & 1]
     const int rows = min(64, n - c * 64);
-    const uint32_t row_bytes = (uint32_t)(nw_e - c_e) * 8u;
-    if (threadIdx.x == 0) mbar_arrive_expect_tx(&full_bar[c & 1], row_bytes * (uint32_t)rows);
-    if ((int)threadIdx.x < rows)
-      bulk_g2s(buf + ((size_t)(c & 1) * 64 + threadIdx.x) * words, M + (size_t)(c * 64 + threadIdx.x) * words + c_e,
-               row_bytes, &full_bar[c & 1]);
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)words * 8u;
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(&full_bar[c & 1], bytes);
+      bulk_g2s(buf + (size_t)(c & 1) * 64 * words, M + (size_t)c * 64 * words, bytes, &full_bar[c & 1]);
+    }
   };
   const bool done0 = s_done != 0;
   int last_issued = -1, last_waited = -1;                     // uniform across the CTA
@@ -459,7 +457,6 @@ __global__ void __launch_bounds__(256) nms_scan_staged_kernel(const unsigned lon
     last_issued = 0;
   }
   for (int c = 0; c < nw && !done0; ++c) {
-    const int c_e = c & ~1;
     mbar_wait(&full_bar[c & 1], ((uint32_t)c >> 1) & 1u);
     last_waited = c;
     if (c + 1 < nw) {                                         // buf[(c+1)&1] was last read in iteration c-1
@@ -478,7 +475,7 @@ __global__ void __launch_bounds__(256) nms_scan_staged_kernel(const unsigned lon
         s_kept[nk++] = b;
         keep[(size_t)p * max_out + total] = c * 64 + b;
         if (++total >= max_out) { s_done = 1; break; }
-        cur |= rows[(size_t)b * words + (c - c_e)];
+        cur |= rows[(size_t)b * words + c];
         avail = ~cur & vmask & ~((2ull << b) - 1ull);
       }
       s_nk = nk; s_total = total;
@@ -488,7 +485,7 @@ __global__ void __launch_bounds__(256) nms_scan_staged_kernel(const unsigned lon
     const int nk = s_nk;
     for (int w = c + 1 + threadIdx.x; w < nw; w += blockDim.x) {
       unsigned long long acc = removed[w];
-      for (int i = 0; i < nk; ++i) acc |= rows[(size_t)s_kept[i] * words + (w - c_e)];
+      for (int i = 0; i < nk; ++i) acc |= rows[(size_t)s_kept[i] * words + w];
       removed[w] = acc;
     }
     __syncthreads();

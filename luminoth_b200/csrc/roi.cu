@@ -7,6 +7,7 @@
 // loads and no conversions; taps shared by the 2x2 samples of a cell are loaded once.  The kernel is
 // instruction / L1-bound (12.8 G bilinear taps per batch at R = 2000), not HBM-bound.
 #include "ops.cuh"
+#include <cstdlib>
 
 namespace lumi {
 
@@ -22,54 +23,61 @@ struct RoiArgs {
 
 struct Samp { int lo, hi; float lerp; int ok; };    // one crop sample coordinate along y or x
 
-__device__ __forceinline__ void load8f(const float* f, size_t off, float (&v)[8]) {
+template <int CPL>
+__device__ __forceinline__ void load8f(const float* f, size_t off, float (&v)[CPL]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(f + off));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(f + off) + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  if (CPL == 8) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(f + off) + 1);
+    v[CPL - 4] = b.x; v[CPL - 3] = b.y; v[CPL - 2] = b.z; v[CPL - 1] = b.w;
+  }
 }
 
 // horizontal lerp of one feature row at the two x samples of a pooled cell; column loads are shared
 // between the two samples whenever they hit the same feature cell (all indices are warp-uniform).
+template <int CPL>
 __device__ __forceinline__ void row_interp(const float* f, size_t rowbase, int c, int c0, const Samp& s0,
-                                           const Samp& s1, float (&h0)[8], float (&h1)[8]) {
-  float l0[8], r0[8], l1[8], r1[8];
-  load8f(f, (rowbase + s0.lo) * c + c0, l0);
-  if (s0.hi != s0.lo) load8f(f, (rowbase + s0.hi) * c + c0, r0);
+                                           const Samp& s1, float (&h0)[CPL], float (&h1)[CPL]) {
+  float l0[CPL], r0[CPL], l1[CPL], r1[CPL];
+  load8f<CPL>(f, (rowbase + s0.lo) * c + c0, l0);
+  if (s0.hi != s0.lo) load8f<CPL>(f, (rowbase + s0.hi) * c + c0, r0);
   else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r0[j] = l0[j];
+    for (int j = 0; j < CPL; ++j) r0[j] = l0[j];
   }
   if (s1.lo == s0.lo) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) l1[j] = l0[j];
+    for (int j = 0; j < CPL; ++j) l1[j] = l0[j];
   } else if (s1.lo == s0.hi) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) l1[j] = r0[j];
+    for (int j = 0; j < CPL; ++j) l1[j] = r0[j];
   } else {
-    load8f(f, (rowbase + s1.lo) * c + c0, l1);
+    load8f<CPL>(f, (rowbase + s1.lo) * c + c0, l1);
   }
   if (s1.hi == s0.hi) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r1[j] = r0[j];
+    for (int j = 0; j < CPL; ++j) r1[j] = r0[j];
   } else if (s1.hi == s1.lo) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r1[j] = l1[j];
+    for (int j = 0; j < CPL; ++j) r1[j] = l1[j];
   } else {
-    load8f(f, (rowbase + s1.hi) * c + c0, r1);
+    load8f<CPL>(f, (rowbase + s1.hi) * c + c0, r1);
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < CPL; ++j) {
     h0[j] = fmaf(r0[j] - l0[j], s0.lerp, l0[j]);      // top + (right - left) * lerp, one rounding fewer than TF
     h1[j] = fmaf(r1[j] - l1[j], s1.lerp, l1[j]);
   }
 }
 
-__global__ void __launch_bounds__(256, 2) roi_pool_kernel(const RoiArgs a) {
+template <int CPL>
+__global__ void __launch_bounds__(256, CPL == 8 ? 2 : 3) roi_pool_kernel(const RoiArgs a) {
+  constexpr int SLICE = 32 * CPL;             // channels per CTA (one warp-wide vector of CPL channels per lane)
   const int row = blockIdx.x;                 // global roi row = img*rmax + r
   const int img = row / a.rmax, r = row % a.rmax;
-  const int cslice = blockIdx.y * 256;
+  const int cslice = blockIdx.y * SLICE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c0 = cslice + lane * 8;
+  const int c0 = cslice + lane * CPL;
   const int oh = a.crop_h >> 1, ow = a.crop_w >> 1;
   const bool live = (a.counts == nullptr || r < a.counts[img]) && c0 < a.c;
   const size_t obase = (size_t)row * oh * ow * a.c;
@@ -98,84 +106,89 @@ __global__ void __launch_bounds__(256, 2) roi_pool_kernel(const RoiArgs a) {
   }
   __syncthreads();
 
-  float msum[8];
+  float msum[CPL];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) msum[j] = 0.f;
+  for (int j = 0; j < CPL; ++j) msum[j] = 0.f;
   for (int cell = warp; cell < oh * ow; cell += 8) {
     if (c0 >= a.c) break;
     const int py = cell / ow, px = cell % ow;
-    float best[8];
+    float best[CPL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) best[j] = live ? -INFINITY : 0.f;
+    for (int j = 0; j < CPL; ++j) best[j] = live ? -INFINITY : 0.f;
     if (live) {
       const Samp y0 = samp[py * 2], y1 = samp[py * 2 + 1];
       const Samp x0 = samp[a.crop_h + px * 2], x1 = samp[a.crop_h + px * 2 + 1];
       // row-interpolated values, shared between the two y samples when they touch the same feature rows
-      float t0[2][8], b0[2][8];          // sample row 0: top / bottom feature row, [sx][ch]
-      row_interp(f, (size_t)y0.lo * a.fw, a.c, c0, x0, x1, t0[0], t0[1]);
-      if (y0.hi != y0.lo) row_interp(f, (size_t)y0.hi * a.fw, a.c, c0, x0, x1, b0[0], b0[1]);
+      float t0[2][CPL], b0[2][CPL];          // sample row 0: top / bottom feature row, [sx][ch]
+      row_interp<CPL>(f, (size_t)y0.lo * a.fw, a.c, c0, x0, x1, t0[0], t0[1]);
+      if (y0.hi != y0.lo) row_interp<CPL>(f, (size_t)y0.hi * a.fw, a.c, c0, x0, x1, b0[0], b0[1]);
       else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { b0[0][j] = t0[0][j]; b0[1][j] = t0[1][j]; }
+        for (int j = 0; j < CPL; ++j) { b0[0][j] = t0[0][j]; b0[1][j] = t0[1][j]; }
       }
 #pragma unroll
       for (int sx = 0; sx < 2; ++sx) {
         const bool ok = y0.ok && (sx ? x1.ok : x0.ok);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < CPL; ++j) {
           const float v = ok ? fmaf(b0[sx][j] - t0[sx][j], y0.lerp, t0[sx][j]) : 0.f;
           best[j] = fmaxf(best[j], v);              // extrapolation_value = 0
         }
       }
-      float t1[2][8], b1[2][8];
+      float t1[2][CPL], b1[2][CPL];
       if (y1.lo == y0.lo) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { t1[0][j] = t0[0][j]; t1[1][j] = t0[1][j]; }
+        for (int j = 0; j < CPL; ++j) { t1[0][j] = t0[0][j]; t1[1][j] = t0[1][j]; }
       } else if (y1.lo == y0.hi) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { t1[0][j] = b0[0][j]; t1[1][j] = b0[1][j]; }
+        for (int j = 0; j < CPL; ++j) { t1[0][j] = b0[0][j]; t1[1][j] = b0[1][j]; }
       } else {
-        row_interp(f, (size_t)y1.lo * a.fw, a.c, c0, x0, x1, t1[0], t1[1]);
+        row_interp<CPL>(f, (size_t)y1.lo * a.fw, a.c, c0, x0, x1, t1[0], t1[1]);
       }
       if (y1.hi == y0.hi) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { b1[0][j] = b0[0][j]; b1[1][j] = b0[1][j]; }
+        for (int j = 0; j < CPL; ++j) { b1[0][j] = b0[0][j]; b1[1][j] = b0[1][j]; }
       } else if (y1.hi == y1.lo) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { b1[0][j] = t1[0][j]; b1[1][j] = t1[1][j]; }
+        for (int j = 0; j < CPL; ++j) { b1[0][j] = t1[0][j]; b1[1][j] = t1[1][j]; }
       } else {
-        row_interp(f, (size_t)y1.hi * a.fw, a.c, c0, x0, x1, b1[0], b1[1]);
+        row_interp<CPL>(f, (size_t)y1.hi * a.fw, a.c, c0, x0, x1, b1[0], b1[1]);
       }
 #pragma unroll
       for (int sx = 0; sx < 2; ++sx) {
         const bool ok = y1.ok && (sx ? x1.ok : x0.ok);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < CPL; ++j) {
           const float v = ok ? fmaf(b1[sx][j] - t1[sx][j], y1.lerp, t1[sx][j]) : 0.f;
           best[j] = fmaxf(best[j], v);
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) msum[j] += best[j];
+    for (int j = 0; j < CPL; ++j) msum[j] += best[j];
     if (a.ohi) {
       uint4 vh, vl;
       __half* qh = reinterpret_cast<__half*>(&vh);
       __half* ql = reinterpret_cast<__half*>(&vl);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) split_f32(best[j], qh[j], ql[j]);
+      for (int j = 0; j < CPL; ++j) split_f32(best[j], qh[j], ql[j]);
       const size_t off = obase + (size_t)cell * a.c + c0;
-      *reinterpret_cast<uint4*>(a.ohi + off) = vh;
-      *reinterpret_cast<uint4*>(a.olo + off) = vl;
+      if (CPL == 8) {
+        *reinterpret_cast<uint4*>(a.ohi + off) = vh;
+        *reinterpret_cast<uint4*>(a.olo + off) = vl;
+      } else {
+        *reinterpret_cast<uint2*>(a.ohi + off) = make_uint2(vh.x, vh.y);
+        *reinterpret_cast<uint2*>(a.olo + off) = make_uint2(vl.x, vl.y);
+      }
     }
   }
   if (a.mhi) {            // fused spatial mean (rcnn.py:188): warp partials -> fixed-order sum -> / cells
-    __shared__ float part[8][256];
+    __shared__ float part[8][SLICE];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) part[warp][lane * 8 + j] = msum[j];
+    for (int j = 0; j < CPL; ++j) part[warp][lane * CPL + j] = msum[j];
     __syncthreads();
     const int ch = cslice + threadIdx.x;
-    if (ch < a.c) {
+    if ((int)threadIdx.x < SLICE && ch < a.c) {
       float s = 0.f;
 #pragma unroll
       for (int w8 = 0; w8 < 8; ++w8) s += part[w8][threadIdx.x];
@@ -201,8 +214,14 @@ void launch_roi_pool(const float* fmap_f32, int n, int fh, int fw, int c, const 
   LUMI_REQUIRE(out.hi || mean.hi, "roi_pool: no output requested");
   long rows = (long)n * rmax;
   if (!rows) return;
-  dim3 grid((unsigned)rows, (unsigned)cdiv(c, 256));
-  roi_pool_kernel<<<grid, 256, 0, st>>>(a);
+  static const int cpl = [] { const char* e = getenv("LUMI_ROI_CPL"); return (e && atoi(e) == 8) ? 8 : 4; }();
+  if (cpl == 8) {
+    dim3 grid((unsigned)rows, (unsigned)cdiv(c, 256));
+    roi_pool_kernel<8><<<grid, 256, 0, st>>>(a);
+  } else {                 // 4 channels per lane: half the registers, twice the resident warps
+    dim3 grid((unsigned)rows, (unsigned)cdiv(c, 128));
+    roi_pool_kernel<4><<<grid, 256, 0, st>>>(a);
+  }
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
