@@ -94,10 +94,10 @@ void nms_workspace_free(NmsWorkspace& ws) {
 __device__ __forceinline__ uint32_t score_key(float s) { return (s >= 0.f) ? (__float_as_uint(s) + 1u) : 0u; }
 
 // ------------------------------------------------------------------ LSD radix sort (one CTA per problem)
-// Stable 8 x 4-bit passes over (key', index) pairs, key' = ~score_key: ascending key' == descending
+// Stable 4 x 8-bit passes over (key', index) pairs, key' = ~score_key: ascending key' == descending
 // score, stability == "ties -> lower index first" (tf.nn.top_k / NMS candidate order).  Each warp owns a
-// contiguous segment and walks it 32 items at a time; 16 ballots give every lane the mask of its digit
-// group (rank inside the round = popc below the lane; __match_any_sync is ~10x slower here), a per-warp
+// contiguous segment and walks it 32 items at a time; 8 ballots (one per digit bit, intersected) give
+// every lane the mask of its digit group (rank inside the round = popc below the lane), a per-warp
 // digit table in shared memory carries the rank across rounds, and one block-wide exclusive scan in
 // digit-major order yields the global offsets.  Two sweeps per pass (count, then scatter) keep register
 // use independent of the problem size; data ping-pongs through L2.
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
                                                                      int* __restrict__ order,
                                                                      int* __restrict__ nvalid) {
   constexpr int U = 4;                                   // rounds fetched ahead (independent loads in flight)
-  constexpr int BITS = 4, BINS = 16, PASSES = 32 / BITS;
+  constexpr int BITS = 8, BINS = 256, PASSES = 32 / BITS;
   __shared__ uint32_t hist[NWARPS][BINS];
   __shared__ uint32_t warp_tot[NWARPS];
   __shared__ int s_count;
@@ -125,11 +125,11 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
   int local_valid = 0;
   // mask of the lanes (among the active ones) that hold the same digit as this lane
   auto group_mask = [&](uint32_t digit, bool act) -> uint32_t {
-    uint32_t mine = 0u;
+    uint32_t mine = __ballot_sync(0xffffffffu, act);
 #pragma unroll
-    for (int d = 0; d < BINS; ++d) {
-      const uint32_t b = __ballot_sync(0xffffffffu, act && digit == (uint32_t)d);
-      if (digit == (uint32_t)d) mine = b;
+    for (int b = 0; b < BITS; ++b) {
+      const uint32_t vote = __ballot_sync(0xffffffffu, (digit >> b) & 1u);
+      mine &= ((digit >> b) & 1u) ? vote : ~vote;
     }
     return mine;
   };
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
       }
       return src[i];
     };
-    if (lane < BINS) hist[warp][lane] = 0;
+    for (int d = lane; d < BINS; d += 32) hist[warp][d] = 0;
     __syncwarp();
     // ---- sweep 1: per-warp digit counts
     for (int base = lo; base < hi; base += 32 * U) {
@@ -163,12 +163,17 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
       }
     }
     __syncthreads();
-    // ---- exclusive scan in digit-major order: entry j = d * NWARPS + w  (BINS * NWARPS <= blockDim entries)
+    // ---- exclusive scan in digit-major order: entry j = d * NWARPS + w, EPT entries per thread
     {
-      const int j = threadIdx.x;
-      const bool has = j < BINS * NWARPS;
-      const uint32_t val = has ? hist[j % NWARPS][j / NWARPS] : 0u;
-      uint32_t incl = val;
+      constexpr int EPT = BINS / 32;                      // BINS * NWARPS / (32 * NWARPS)
+      uint32_t v[EPT], sum = 0;
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int j = threadIdx.x * EPT + e;
+        v[e] = hist[j % NWARPS][j / NWARPS];
+        sum += v[e];
+      }
+      uint32_t incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -178,7 +183,13 @@ __global__ void __launch_bounds__(NWARPS * 32) sort_desc_radix_kernel(const floa
       __syncthreads();
       uint32_t wbase = 0;
       for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
-      if (has) hist[j % NWARPS][j / NWARPS] = wbase + incl - val;
+      uint32_t run = wbase + incl - sum;
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int j = threadIdx.x * EPT + e;
+        hist[j % NWARPS][j / NWARPS] = run;
+        run += v[e];
+      }
     }
     __syncthreads();
     // ---- sweep 2: stable scatter
