@@ -144,7 +144,7 @@ def run_reference(args, wl):
             'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
                              'sample': '%d images, one per step (oracle port of the reference forward; TF1 not installable)' % done},
             'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def run_ours(args, wl):
@@ -311,8 +311,10 @@ def run_ours(args, wl):
             out['cpu_baseline'] = {'value': cv, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
                                    'sample': '%d images of the same workload, one at a time, %.1f s '
                                              '(oracle port of the reference forward; TF1 not installable)' % (n_cpu, cdt)}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     eng.close()
+    del imgs_dev, imgs_host, boxes, scores, labels, counts, rec, gathered, hb, hs, hl, hc
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -335,6 +337,11 @@ def main():
         from luminoth_b200.engine import load_library
         load_library()          # fail loudly if the CUDA library is missing
         run_ours(args, wl)
+        # The engine library carries its own (static) CUDA runtime next to torch's; skip the interpreter's
+        # static-destructor phase, where the two runtimes tear the primary context down in an undefined order.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':

@@ -83,6 +83,11 @@ const char* lumi_profile_read(lumi_engine* e);
  * 1 = tcgen05 fp16x2-split tensor-core kernel wherever the layer qualifies (default). */
 int lumi_set_conv_impl(lumi_engine* e, int impl);
 
+/* 1 (default): lumi_predict splits the batch in two halves that run on two streams, so the latency-bound
+ * proposal / NMS kernels of one half overlap the convolutions of the other. 0: single stream. Results are
+ * identical either way (images are independent). Off automatically while profiling or tapping. */
+int lumi_set_pipeline(lumi_engine* e, int enable);
+
 /* 1: also materialise intermediates the fused production path never writes (the "roi_pool" tap when
  * ROI crop + max-pool + mean run as one kernel) -- config.train.debug in the reference. Default 0. */
 int lumi_set_debug_taps(lumi_engine* e, int enable);

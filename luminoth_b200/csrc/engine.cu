@@ -104,7 +104,12 @@ struct lumi_engine {
   int ssd_total_anchors = 0;
   int fixed_h = 300, fixed_w = 300;
 
-  Arena arena;
+  Arena arena, arena2;          // arena2: second half-batch when the forward is software-pipelined
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float* d_final_keys2 = nullptr;
+  int pipeline = 1;             // 1: split the batch in two and run the halves on two streams (hides the
+                                // latency-bound proposal / NMS kernels of one half under the other half's convs)
   int* d_overflow = nullptr;
   uint8_t* d_images = nullptr; size_t images_cap = 0;
   float* d_boxes = nullptr; float* d_scores = nullptr; int* d_labels = nullptr; int* d_counts = nullptr;
@@ -123,7 +128,10 @@ struct lumi_engine {
     for (auto& kv : dev_vecs) cudaFree(kv.second);
     nms_workspace_free(ws_rpn); nms_workspace_free(ws_det);
     cudaFree(d_anchor_ref); cudaFree(d_anchors); cudaFree(d_final_keys); cudaFree(d_ssd_anchors);
-    cudaFree(arena.base); cudaFree(d_overflow); cudaFree(d_images);
+    cudaFree(arena.base); cudaFree(arena2.base); cudaFree(d_final_keys2); cudaFree(d_overflow); cudaFree(d_images);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (stream2) cudaStreamDestroy(stream2);
     cudaFree(d_boxes); cudaFree(d_scores); cudaFree(d_labels); cudaFree(d_counts); cudaFree(d_prop_counts);
     for (auto& sp : prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto ev : prof_pool) cudaEventDestroy(ev);
@@ -504,27 +512,51 @@ struct Ctx {
   lumi_engine* e;
   bool dry;
   cudaStream_t st;
+  Arena* arena = nullptr;       // workspace of this (half-)batch
+  int img_off = 0;              // first image of this (half-)batch inside the engine-level batch buffers
+  float* final_keys = nullptr;  // scratch of the final top-k sort
+  bool taps = true;             // record debug taps (first half only)
   Act act(int n, int h, int w, int c) {
     Act a; a.n = n; a.h = h; a.w = w; a.c = c;
     const size_t bytes = a.numel() * sizeof(__half);
-    a.hi = (__half*)e->arena.alloc(bytes, dry);
-    a.lo = (__half*)e->arena.alloc(bytes, dry);
+    a.hi = (__half*)arena->alloc(bytes, dry);
+    a.lo = (__half*)arena->alloc(bytes, dry);
     return a;
   }
-  float* f32(size_t count) { return (float*)e->arena.alloc(count * sizeof(float), dry); }
+  float* f32(size_t count) { return (float*)arena->alloc(count * sizeof(float), dry); }
   void tap_f32(const std::string& name, const float* p, int64_t a, int64_t b, int64_t c, int64_t d) {
+    if (!taps) return;
     Tap t; t.ptr = p; t.kind = 0; t.shape[0] = a; t.shape[1] = b; t.shape[2] = c; t.shape[3] = d;
     e->taps[name] = t;
   }
   void tap_act(const std::string& name, Act a) {
+    if (!taps) return;
     Tap t; t.kind = 1; t.act = a; t.shape[0] = a.n; t.shape[1] = a.h; t.shape[2] = a.w; t.shape[3] = a.c;
     e->taps[name] = t;
   }
   void tap_i32(const std::string& name, const int* p, int64_t a) {
+    if (!taps) return;
     Tap t; t.ptr = p; t.kind = 2; t.shape[0] = a; t.shape[1] = 1; t.shape[2] = 1; t.shape[3] = 1;
     e->taps[name] = t;
   }
 };
+
+// problems [off, ...) of a batched NMS workspace (the second half-batch works on its own slice)
+NmsWorkspace ws_view(const NmsWorkspace& ws, int off) {
+  NmsWorkspace v = ws;
+  v.problems = ws.problems - off;
+  v.keys = ws.keys + (size_t)off * ws.cap;
+  v.boxes = ws.boxes + (size_t)off * ws.cap * 4;
+  v.order = ws.order + (size_t)off * ws.cap;
+  v.nvalid = ws.nvalid + off;
+  v.sboxes = ws.sboxes + (size_t)off * ws.ncap * 4;
+  v.sscores = ws.sscores + (size_t)off * ws.ncap;
+  v.mask = ws.mask + (size_t)off * ws.ncap * ws.words;
+  v.keep = ws.keep + (size_t)off * ws.max_out;
+  v.nkeep = ws.nkeep + off;
+  v.sort_tmp = ws.sort_tmp + (size_t)off * 2 * ws.cap;
+  return v;
+}
 
 // padding: 0 VALID, 1 SAME, 2 slim conv2d_same (explicit pad + VALID when stride > 1)
 Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* res, int res_stride, float** out_f32,
@@ -594,8 +626,26 @@ Act bottleneck(Ctx& cx, const std::string& s, Act x, int depth) {
 }
 
 // ---------------------------------------------------------------- Faster R-CNN forward
+void ensure_frcnn_anchors(lumi_engine* e, int h, int w, cudaStream_t st) {
+  // fasterrcnn.py:261-308; the grid follows the block3 feature map: four ceil-halvings of the image size
+  const int fh = cdiv(h, 16), fw = cdiv(w, 16);
+  if (e->anchors_fh == fh && e->anchors_fw == fw) return;
+  const int na = fh * fw * e->A;
+  cudaFree(e->d_anchors);
+  e->d_anchors = nullptr;
+  LUMI_CUDA_CHECK(cudaMalloc(&e->d_anchors, (size_t)na * 4 * sizeof(float)));
+  launch_frcnn_anchors(e->d_anchor_ref, e->A, fh, fw, e->anchor_stride, e->d_anchors, st);
+  e->anchors_fh = fh; e->anchors_fw = fw;
+}
+
 void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   lumi_engine* e = cx.e;
+  const int io = cx.img_off;                      // this (half-)batch's slice of the engine-level buffers
+  int* prop_counts = e->d_prop_counts + io;
+  float* out_boxes = e->d_boxes + (size_t)io * e->kmax * 4;
+  float* out_scores = e->d_scores + (size_t)io * e->kmax;
+  int* out_labels = e->d_labels + (size_t)io * e->kmax;
+  int* out_counts = e->d_counts + io;
   const std::string root = "truncated_base_network/" + e->arch;
   const int* units = e->arch == "resnet_v1_50" ? RESNET_UNITS_50 : RESNET_UNITS_101;
   Act x;
@@ -622,15 +672,9 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   cx.tap_act("conv_feature_map", fmap);
   const int fh = fmap.h, fw = fmap.w;
 
-  // anchors (fasterrcnn.py:261-308), regenerated only when the feature-map shape changes
+  // anchors (fasterrcnn.py:261-308): made by ensure_frcnn_anchors() before the forward starts
   const int na = fh * fw * e->A;
-  if (!cx.dry && (e->anchors_fh != fh || e->anchors_fw != fw)) {
-    cudaFree(e->d_anchors);
-    e->d_anchors = nullptr;
-    LUMI_CUDA_CHECK(cudaMalloc(&e->d_anchors, (size_t)na * 4 * sizeof(float)));
-    launch_frcnn_anchors(e->d_anchor_ref, e->A, fh, fw, e->anchor_stride, e->d_anchors, cx.st);
-    e->anchors_fh = fh; e->anchors_fw = fw;
-  }
+  if (!cx.dry) LUMI_REQUIRE(e->anchors_fh == fh && e->anchors_fw == fw, "anchor grid mismatch (internal)");
   cx.tap_f32("all_anchors", e->d_anchors, na, 4, 1, 1);
 
   // RPN (rpn.py:136-180): 3x3 conv + act, fused 1x1 heads [cls 2A | bbox 4A], softmax fused into the decode
@@ -648,27 +692,28 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   float* pscores = cx.f32((size_t)n * post);
   if (!cx.dry) {
     LUMI_REQUIRE(na <= e->ws_rpn.cap, "image too large for the RPN workspace (max_h/max_w at lumi_create)");
+    NmsWorkspace wsr = ws_view(e->ws_rpn, io);
     // algorithmic bytes: decode N*(36 in + 20 out), sort N*4 + K*20, bitmask NMS K*16 + 2*K*ceil(K/64)*8 + P*4
     const double kk = std::min(na, rp.pre_nms_top_n);
     const double bytes = (double)n * (56.0 * na + 4.0 * na + 20.0 * kk + 16.0 * kk + 16.0 * kk * std::ceil(kk / 64.0) + 4.0 * post);
     ProfScope ps(cx.e, cx.dry, PC_RPN_POST, bytes);
-    launch_rpn_proposals(heads, heads, (long)fh * fw * hc, (long)fh * fw * hc, e->A, e->d_anchors, n, rp, e->ws_rpn,
-                         proposals, pscores, e->d_prop_counts, cx.st);
+    launch_rpn_proposals(heads, heads, (long)fh * fw * hc, (long)fh * fw * hc, e->A, e->d_anchors, n, rp, wsr,
+                         proposals, pscores, prop_counts, cx.st);
   }
   cx.tap_f32("proposals", proposals, n, post, 4, 1);
   cx.tap_f32("proposal_scores", pscores, n, post, 1, 1);
-  cx.tap_i32("proposal_counts", e->d_prop_counts, n);
+  cx.tap_i32("proposal_counts", prop_counts, n);
   cx.tap_f32("rpn_sorted_scores", e->ws_rpn.sscores, n, e->ws_rpn.ncap, 1, 1);
   cx.tap_i32("rpn_sorted_counts", e->ws_rpn.nvalid, n);
 
   if (!e->with_rcnn) {
     if (!cx.dry) {     // predicting.py:85-92: objects = proposals, probs = scores, labels = 0
-      LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_boxes, proposals, (size_t)n * post * 4 * sizeof(float),
+      LUMI_CUDA_CHECK(cudaMemcpyAsync(out_boxes, proposals, (size_t)n * post * 4 * sizeof(float),
                                       cudaMemcpyDeviceToDevice, cx.st));
-      LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_scores, pscores, (size_t)n * post * sizeof(float), cudaMemcpyDeviceToDevice,
+      LUMI_CUDA_CHECK(cudaMemcpyAsync(out_scores, pscores, (size_t)n * post * sizeof(float), cudaMemcpyDeviceToDevice,
                                       cx.st));
-      LUMI_CUDA_CHECK(cudaMemsetAsync(e->d_labels, 0, (size_t)n * post * sizeof(int), cx.st));
-      LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_counts, e->d_prop_counts, n * sizeof(int), cudaMemcpyDeviceToDevice, cx.st));
+      LUMI_CUDA_CHECK(cudaMemsetAsync(out_labels, 0, (size_t)n * post * sizeof(int), cx.st));
+      LUMI_CUDA_CHECK(cudaMemcpyAsync(out_counts, prop_counts, n * sizeof(int), cudaMemcpyDeviceToDevice, cx.st));
     }
     return;
   }
@@ -687,7 +732,7 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
                          4.0 * (double)(fuse_mean ? feat.numel() : 0);
     ProfScope ps(cx.e, cx.dry, PC_ROI, bytes);
     launch_act_to_f32(fmap, fmap_f32, cx.st);
-    launch_roi_pool(fmap_f32, fmap.n, fmap.h, fmap.w, fmap.c, proposals, e->d_prop_counts, post, (float)h, (float)w,
+    launch_roi_pool(fmap_f32, fmap.n, fmap.h, fmap.w, fmap.c, proposals, prop_counts, post, (float)h, (float)w,
                     e->pooled_h, e->pooled_w, pooled, fuse_mean ? feat : Act(), cx.st);
   }
   if (need_pooled) cx.tap_act("roi_pool", pooled);
@@ -719,8 +764,9 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   dp.prob_stride = C + 1; dp.delta_stride = fcw;
   if (!cx.dry) {
     ProfScope ps(cx.e, cx.dry, PC_DET_POST);
-    launch_class_detections(proposals, (long)post * 4, e->d_prop_counts, fc + (C + 1), cls_prob, n, dp, e->ws_det,
-                            e->d_final_keys, e->d_boxes, e->d_labels, e->d_scores, e->d_counts, cx.st);
+    NmsWorkspace wsd = ws_view(e->ws_det, io * C);
+    launch_class_detections(proposals, (long)post * 4, prop_counts, fc + (C + 1), cls_prob, n, dp, wsd, cx.final_keys,
+                            out_boxes, out_labels, out_scores, out_counts, cx.st);
   }
 }
 
@@ -844,16 +890,39 @@ void forward_ssd(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   dp.r = total; dp.im_h = (float)h; dp.im_w = (float)w; dp.prob_stride = C1; dp.delta_stride = 4;
   if (!cx.dry) {
     ProfScope ps(cx.e, cx.dry, PC_DET_POST);
-    launch_class_detections(e->d_ssd_anchors, 0, nullptr, loc, prob, n, dp, e->ws_det, e->d_final_keys, e->d_boxes,
-                            e->d_labels, e->d_scores, e->d_counts, cx.st);
+    const int io = cx.img_off;
+    NmsWorkspace wsd = ws_view(e->ws_det, io * e->num_classes);
+    launch_class_detections(e->d_ssd_anchors, 0, nullptr, loc, prob, n, dp, wsd, cx.final_keys,
+                            e->d_boxes + (size_t)io * e->kmax * 4, e->d_labels + (size_t)io * e->kmax,
+                            e->d_scores + (size_t)io * e->kmax, e->d_counts + io, cx.st);
   }
 }
 
 void forward(Ctx& cx, const uint8_t* images, int n, int h, int w) {
-  cx.e->arena.off = 0;
-  cx.e->taps.clear();
+  cx.arena->off = 0;
+  if (cx.taps) cx.e->taps.clear();
   if (cx.e->type == "fasterrcnn") forward_frcnn(cx, images, n, h, w);
   else forward_ssd(cx, images, n, h, w);
+}
+
+Ctx make_ctx(lumi_engine* e, bool dry, int half) {
+  Ctx cx;
+  cx.e = e; cx.dry = dry;
+  cx.st = half ? e->stream2 : e->stream;
+  cx.arena = half ? &e->arena2 : &e->arena;
+  cx.final_keys = half ? e->d_final_keys2 : e->d_final_keys;
+  cx.taps = half == 0;
+  return cx;
+}
+
+void ensure_arena(lumi_engine* e, Arena& a, size_t need_bytes) {
+  if (need_bytes <= a.cap) return;
+  LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  if (e->stream2) LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream2));
+  cudaFree(a.base);
+  a.base = nullptr; a.cap = 0;
+  LUMI_CUDA_CHECK(cudaMalloc(&a.base, need_bytes));
+  a.cap = need_bytes;
 }
 
 int fail(lumi_engine* e, const Error& err) {
@@ -980,6 +1049,13 @@ int lumi_finalize(lumi_engine* e) {
     nms_workspace_alloc(e->ws_det, nb * e->num_classes, e->ssd_total_anchors, e->det.class_max);
     LUMI_CUDA_CHECK(cudaMalloc(&e->d_final_keys, det_final_scratch_bytes(nb, e->num_classes, e->det.class_max)));
   }
+  if (e->max_batch >= 2) {
+    LUMI_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    LUMI_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    LUMI_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    if (e->d_final_keys)
+      LUMI_CUDA_CHECK(cudaMalloc(&e->d_final_keys2, det_final_scratch_bytes(nb, e->num_classes, e->det.class_max)));
+  }
   e->finalized = true;
   return LUMI_OK;
   LUMI_API_END(e)
@@ -994,19 +1070,17 @@ int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n
   LUMI_REQUIRE(n > 0 && n <= e->max_batch, "lumi_predict: batch size exceeds max_batch");
   LUMI_REQUIRE(h > 0 && w > 0 && h <= e->max_h && w <= e->max_w, "lumi_predict: image larger than max_h x max_w");
   LUMI_CUDA_CHECK(cudaSetDevice(e->device));
-  Ctx cx{e, false, e->stream};
-  if (n != e->planned_n || h != e->planned_h || w != e->planned_w) {   // size the arena for this shape
-    Ctx dry{e, true, e->stream};
-    forward(dry, nullptr, n, h, w);
+  // software pipelining: two half-batches on two streams (off while profiling / tapping intermediates)
+  const bool piped = e->pipeline && n >= 2 && !e->profile && !e->debug_taps && e->stream2 != nullptr;
+  const int nA = piped ? (n + 1) / 2 : n, nB = n - nA;
+  const int plan_key = piped ? -n : n;
+  if (plan_key != e->planned_n || h != e->planned_h || w != e->planned_w) {   // size the arenas for this shape
+    Ctx dry = make_ctx(e, true, 0);
+    forward(dry, nullptr, nA, h, w);
     const size_t need_bytes = e->arena.off + 4096;
-    if (need_bytes > e->arena.cap) {
-      LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-      cudaFree(e->arena.base);
-      e->arena.base = nullptr; e->arena.cap = 0;
-      LUMI_CUDA_CHECK(cudaMalloc(&e->arena.base, need_bytes));
-      e->arena.cap = need_bytes;
-    }
-    e->planned_n = n; e->planned_h = h; e->planned_w = w;
+    ensure_arena(e, e->arena, need_bytes);
+    if (piped) ensure_arena(e, e->arena2, need_bytes);
+    e->planned_n = plan_key; e->planned_h = h; e->planned_w = w;
   }
   const uint8_t* dimg = static_cast<const uint8_t*>(images);
   const size_t img_bytes = (size_t)n * h * w * 3;
@@ -1022,7 +1096,21 @@ int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n
     dimg = e->d_images;
   }
   g_launch_count = 0;
-  forward(cx, dimg, n, h, w);
+  if (e->type == "fasterrcnn") ensure_frcnn_anchors(e, h, w, e->stream);
+  Ctx cx = make_ctx(e, false, 0);
+  if (piped) {
+    LUMI_CUDA_CHECK(cudaEventRecord(e->ev_fork, e->stream));
+    LUMI_CUDA_CHECK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+    Ctx cb = make_ctx(e, false, 1);
+    cb.img_off = nA;
+    // interleave nothing on the host: the two forwards are enqueued back to back, the GPU overlaps them
+    forward(cx, dimg, nA, h, w);
+    forward(cb, dimg + (size_t)nA * h * w * 3, nB, h, w);
+    LUMI_CUDA_CHECK(cudaEventRecord(e->ev_join, e->stream2));
+    LUMI_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+  } else {
+    forward(cx, dimg, n, h, w);
+  }
   e->launches = g_launch_count;
   const size_t k = (size_t)e->kmax;
   const cudaMemcpyKind kind = outputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -1064,6 +1152,12 @@ int lumi_synchronize(lumi_engine* e) {
 }
 
 int lumi_last_launch_count(lumi_engine* e) { return e ? e->launches : 0; }
+
+int lumi_set_pipeline(lumi_engine* e, int enable) {
+  if (!e) return LUMI_EINVAL;
+  e->pipeline = enable != 0;
+  return LUMI_OK;
+}
 
 int lumi_set_debug_taps(lumi_engine* e, int enable) {
   if (!e) return LUMI_EINVAL;

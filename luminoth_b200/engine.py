@@ -44,6 +44,7 @@ SIGNATURES = {
     'lumi_last_launch_count': (ctypes.c_int, [ctypes.c_void_p]),
     'lumi_set_conv_impl': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'lumi_set_debug_taps': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    'lumi_set_pipeline': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'lumi_profile_enable': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'lumi_profile_read': (ctypes.c_char_p, [ctypes.c_void_p]),
     'lumi_get_tensor': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, _c_i64_p,
@@ -212,6 +213,9 @@ class Engine(object):
                                         ctypes.c_void_p(labels.data_ptr()), ctypes.c_void_p(counts.data_ptr()), 1)
             if rc != LUMI_OK:
                 _raise(rc, self._lib.lumi_last_error(self._h))
+
+    def set_pipeline(self, enable=True):
+        self._lib.lumi_set_pipeline(self._h, int(bool(enable)))
 
     def set_debug_taps(self, enable=True):
         self._lib.lumi_set_debug_taps(self._h, int(bool(enable)))

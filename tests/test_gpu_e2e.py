@@ -150,7 +150,11 @@ def test_ssd_stages_and_detections(impl):
     eng = Engine(cfg, max_batch=2)
     eng.load_weights(wts).finalize()
     eng.set_conv_impl(impl)
+    piped = eng.predict_raw(imgs)                      # production path: two half-batches on two streams
+    eng.set_debug_taps(True)                           # single stream, taps cover the whole batch
     boxes, scores, labels, counts = eng.predict_raw(imgs)
+    for a, b in zip(piped, (boxes, scores, labels, counts)):
+        np.testing.assert_array_equal(a, b)            # pipelining must not change the result
     loc = eng.get_tensor('loc_pred'); prob = eng.get_tensor('cls_prob'); anchors = eng.get_tensor('all_anchors')
     for i in range(2):
         ref = ossd.forward(imgs[i], wts, cfg)
