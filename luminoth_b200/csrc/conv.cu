@@ -19,6 +19,7 @@
 // models/ssd/feature_extractor.py:28-37) and snt.Linear (models/fasterrcnn/rcnn.py:74-98).
 #include "conv.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -673,6 +674,10 @@ bool conv_tc_supported(const ConvLayer& L, const ConvIO& io) {
   return true;
 }
 
+// SMs a persistent conv launch may occupy.  While the engine runs its two-stream pipeline it leaves
+// g_conv_sm_reserve SMs free so the few-CTA latency-bound kernels (sort, NMS scan) of the other half-batch
+// run concurrently instead of waiting behind a 148-CTA persistent grid (measured +1.7 % images/s at 8-16).
+int g_conv_sm_reserve = 0;
 static int sm_count() {
   static int n = 0;
   if (!n) {
@@ -680,7 +685,8 @@ static int sm_count() {
     LUMI_CUDA_CHECK(cudaGetDevice(&dev));
     LUMI_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
   }
-  return n;
+  const int r = g_conv_sm_reserve;
+  return (r > 0 && r < n) ? n - r : n;
 }
 
 template <int BN, int STAGES, bool RES>

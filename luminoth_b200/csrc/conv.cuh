@@ -41,6 +41,7 @@ struct ConvIO {
 void conv_layer_upload(ConvLayer& L, const float* w_host, const float* scale_host, const float* bias_host);
 void conv_layer_free(ConvLayer& L);
 
+extern int g_conv_sm_reserve;     // SMs left free by persistent conv launches (set by the engine's pipeline)
 bool conv_tc_supported(const ConvLayer& L, const ConvIO& io);
 void launch_conv_simt(const ConvLayer& L, const ConvIO& io, cudaStream_t st);
 void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st);

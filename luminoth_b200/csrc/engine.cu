@@ -1098,6 +1098,7 @@ int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n
   g_launch_count = 0;
   if (e->type == "fasterrcnn") ensure_frcnn_anchors(e, h, w, e->stream);
   Ctx cx = make_ctx(e, false, 0);
+  g_conv_sm_reserve = piped ? 8 : 0;
   if (piped) {
     LUMI_CUDA_CHECK(cudaEventRecord(e->ev_fork, e->stream));
     LUMI_CUDA_CHECK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
