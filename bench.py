@@ -312,12 +312,16 @@ def run_ours(args, wl):
                                    'sample': '%d images of the same workload, one at a time, %.1f s '
                                              '(oracle port of the reference forward; TF1 not installable)' % (n_cpu, cdt)}
         print(json.dumps(out), flush=True)
-    eng.close()
-    del imgs_dev, imgs_host, boxes, scores, labels, counts, rec, gathered, hb, hs, hl, hc
+    # teardown order matters: tensors that lived on the engine's (external) stream must be released, and the
+    # process group torn down, BEFORE the engine destroys that stream
+    eng.synchronize()
+    del imgs_dev, imgs_host, boxes, scores, labels, counts, rec, gathered, hb, hs, hl, hc, stream
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    eng.close()
 
 
 def main():

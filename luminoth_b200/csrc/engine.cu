@@ -1084,6 +1084,7 @@ int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n
   }
   const uint8_t* dimg = static_cast<const uint8_t*>(images);
   const size_t img_bytes = (size_t)n * h * w * 3;
+  const size_t bytes_a = (size_t)nA * h * w * 3;
   if (!images_on_device) {
     if (img_bytes > e->images_cap) {
       LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
@@ -1092,7 +1093,6 @@ int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n
       LUMI_CUDA_CHECK(cudaMalloc(&e->d_images, img_bytes));
       e->images_cap = img_bytes;
     }
-    LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_images, images, img_bytes, cudaMemcpyHostToDevice, e->stream));
     dimg = e->d_images;
   }
   g_launch_count = 0;
@@ -1104,12 +1104,19 @@ int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n
     LUMI_CUDA_CHECK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
     Ctx cb = make_ctx(e, false, 1);
     cb.img_off = nA;
-    // interleave nothing on the host: the two forwards are enqueued back to back, the GPU overlaps them
+    // each half uploads its own images on its own stream: the second half's H2D overlaps the first half's kernels
+    if (!images_on_device) {
+      LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_images, images, bytes_a, cudaMemcpyHostToDevice, e->stream));
+      LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_images + bytes_a, static_cast<const uint8_t*>(images) + bytes_a,
+                                      img_bytes - bytes_a, cudaMemcpyHostToDevice, e->stream2));
+    }
     forward(cx, dimg, nA, h, w);
-    forward(cb, dimg + (size_t)nA * h * w * 3, nB, h, w);
+    forward(cb, dimg + bytes_a, nB, h, w);
     LUMI_CUDA_CHECK(cudaEventRecord(e->ev_join, e->stream2));
     LUMI_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
   } else {
+    if (!images_on_device)
+      LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_images, images, img_bytes, cudaMemcpyHostToDevice, e->stream));
     forward(cx, dimg, n, h, w);
   }
   e->launches = g_launch_count;
