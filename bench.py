@@ -90,6 +90,18 @@ class ClockSampler(threading.Thread):
                 'reasons': reasons, 'samples': len(sm)}
 
 
+def conv_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the conv_tc launches of one step, from the committed
+    ncu --set full capture of `bench.py --ncu-range` (profiles/r1_ncu_step_summary.json); None if not captured."""
+    f = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_step_summary.json')
+    try:
+        d = json.load(open(f))[workload]['conv_tc_kernel']
+        return d['dram_bytes'], ('sum of dram__bytes_read+write over the %d conv_tc launches of one step '
+                                 '(profiles/r1_ncu_step_summary.json)' % d['launches'])
+    except Exception:
+        return None, 'not captured'
+
+
 def build_config(wl):
     from luminoth_b200 import default_config
     return default_config(wl['model'], wl['overrides'])
@@ -242,6 +254,22 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
         return float(ms.item())
 
+    if args.ncu_range:
+        # evidence mode for `ncu --profile-from-start off`: warm up, then expose exactly ONE step to the profiler
+        for i in range(args.warmup):
+            step_device(i)
+        eng.synchronize()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_device(args.warmup)
+        eng.synchronize()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        del imgs_dev, imgs_host, boxes, scores, labels, counts, rec, gathered, hb, hs, hl, hc, stream
+        torch.cuda.synchronize()
+        eng.close()
+        return
+
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -271,7 +299,8 @@ def run_ours(args, wl):
             ach = tc_flops / (tc_ms * 1e-3) / 1e12
             roof = {'kernel': 'conv_tc_kernel (tcgen05 implicit-GEMM conv, all instances of one step)',
                     'bound': 'tensor', 'achieved': ach, 'peak': tf, 'unit': 'TFLOP/s', 'frac': ach / tf,
-                    'peak_source': src + ', bf16 sustained', 'traffic': None,
+                    'peak_source': src + ', bf16 sustained', 'traffic': conv_traffic(args.workload)[0],
+                    'traffic_note': conv_traffic(args.workload)[1],
                     'launches_per_step': tc_spans / args.steps,
                     'algorithmic_gflop_per_step': tc_flops / args.steps / 1e9,
                     'ms_per_step': tc_ms / args.steps,
@@ -332,6 +361,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='frcnn_r50', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ncu-range', action='store_true',
+                    help='run warm-up, then one step inside cudaProfilerStart/Stop (for ncu --profile-from-start off)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     wl = WORKLOADS[args.workload]

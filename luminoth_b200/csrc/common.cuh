@@ -57,6 +57,18 @@ __device__ __forceinline__ void split_f32(float x, __half& hi, __half& lo) {
 __device__ __forceinline__ float join_f16(__half hi, __half lo) {
   return __half2float(hi) + __half2float(lo);
 }
+// x - float(h) in one mixed-precision FHFMA (sm_100: fma.f32.f16).  With h = rn16(x) the difference is
+// exactly representable in fp32, so this equals the two-instruction cvt + sub bit for bit.
+__device__ __forceinline__ float sub_f32_f16(float x, __half h) {
+  float d;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(__half_as_ushort(h)), "h"((unsigned short)0xBC00), "f"(x));
+  return d;
+}
+// two values per cvt.rn.f16x2.f32: hi = rn16(v), lo = rn16(v - hi)   (same results as split_f32)
+__device__ __forceinline__ void split2_f32(float a, float b, __half2& hi, __half2& lo) {
+  hi = __floats2half2_rn(a, b);
+  lo = __floats2half2_rn(sub_f32_f16(a, __low2half(hi)), sub_f32_f16(b, __high2half(hi)));
+}
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.f);
   if (act == ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);

@@ -237,6 +237,7 @@ struct TcCfg {
 };
 
 constexpr int TC_THREADS = 320;                     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_THREADS_RES = 352;                 // + warp 10: residual-tile TMA producer (RES kernels)
 
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, += gridDim.x.  The
 // TMA producer, the MMA issuer and the epilogue warps each iterate the same tile sequence with
@@ -244,10 +245,12 @@ constexpr int TC_THREADS = 320;                     // warp 0 TMA, warp 1 MMA, w
 // tensor core starts the next tile while the epilogue warps are still storing the previous one
 // (D1 and D2 are double-buffered in TMEM).
 template <int BN, int STAGES, bool RES>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+__global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   using Cfg = TcCfg<BN, STAGES, RES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024 B alignment by OFFSET (not by integer round-trip) so the compiler keeps the shared address space
+  // and emits LDS/STS for the staging buffers instead of generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES;      // [2 halves][hi, lo][128 rows x 64 B], 64 B swizzle
   uint8_t* res_stage = out_stage + Cfg::OUT_STAGE_BYTES;      // [BN/32 slabs][hi, lo][128 rows x 64 B] (RES only)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_stage + Cfg::RES_STAGE_BYTES);
@@ -255,9 +258,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint64_t* acc_full_bar = empty_bar + STAGES;       // [2]  D1[buf] chunk complete (tcgen05.commit)
   uint64_t* acc_empty_bar = acc_full_bar + 2;        // [2]  D1[buf] drained by the 8 epilogue warps
   uint64_t* d2_empty_bar = acc_empty_bar + 2;        // [2]  D2[tbuf] drained
-  uint64_t* res_full_bar = d2_empty_bar + 2;         // residual tile landed (TMA)
-  uint64_t* res_empty_bar = res_full_bar + 1;        // residual tile consumed by the 8 epilogue warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty_bar + 1);
+  uint64_t* res_full_bar = d2_empty_bar + 2;         // [4]  residual slab landed (TMA)
+  uint64_t* res_empty_bar = res_full_bar + 4;        // [4]  residual slab consumed by its 4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty_bar + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full_bar[s], 1); mbar_init(&acc_empty_bar[s], 8); mbar_init(&d2_empty_bar[s], 8);
     }
-    mbar_init(res_full_bar, 1); mbar_init(res_empty_bar, 8);
+    for (int s = 0; s < 4; ++s) { mbar_init(&res_full_bar[s], 1); mbar_init(&res_empty_bar[s], 4); }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -297,17 +300,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int nt = t % a.n_tiles, mt = t / a.n_tiles;
         const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
         const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
-        if (RES) {        // residual tile of THIS tile: needed only by its epilogue, so it streams in under the K loop
-          mbar_wait(res_empty_bar, (tile_iter & 1u) ^ 1u);
-          mbar_arrive_expect_tx(res_full_bar, (uint32_t)(BN / 32) * 2u * (uint32_t)rows_valid * 64u);
-#pragma unroll
-          for (int sl = 0; sl < BN / 32; ++sl) {
-            tma_load_4d(res_stage + (sl * 2 + 0) * 8192, &a.tm_r_hi, res_full_bar, n0 + sl * 32, x0 * a.res_stride,
-                        y0 * a.res_stride, img0);
-            tma_load_4d(res_stage + (sl * 2 + 1) * 8192, &a.tm_r_lo, res_full_bar, n0 + sl * 32, x0 * a.res_stride,
-                        y0 * a.res_stride, img0);
-          }
-        }
         for (int tap = 0; tap < a.kh * a.kw; ++tap) {
           const int r = tap / a.kw, s = tap % a.kw;
           const int iy = y0 * a.stride + r * a.rate - a.pad_t, ix = x0 * a.stride + s * a.rate - a.pad_l;
@@ -364,6 +356,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             umma_commit(&acc_full_bar[buf]);            // D1[buf] (and, on the last chunk, D2[tbuf]) complete
             ++gchunk;
           }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    if (RES && lane == 0) {
+      // ---------------- residual producer: the shortcut tile of each output tile, one 32-channel slab (hi + lo
+      // plane) per barrier pair, refilled as soon as its four epilogue warps have read the previous tile's slab.
+      // It runs on its own warp so that it never holds back the operand loads of the next tile.
+      const uint32_t slab_tx = 2u * (uint32_t)rows_valid * 64u;
+      uint32_t tile_iter = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+        const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+        const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
+        const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) {
+          // consumption order: both column halves work on their first slab, then on their second
+          const int sl = (i % 2) * (BN / 64) + (i / 2);
+          mbar_wait(&res_empty_bar[sl], (tile_iter & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&res_full_bar[sl], slab_tx);
+          tma_load_4d(res_stage + (sl * 2 + 0) * 8192, &a.tm_r_hi, &res_full_bar[sl], n0 + sl * 32,
+                      x0 * a.res_stride, y0 * a.res_stride, img0);
+          tma_load_4d(res_stage + (sl * 2 + 1) * 8192, &a.tm_r_lo, &res_full_bar[sl], n0 + sl * 32,
+                      x0 * a.res_stride, y0 * a.res_stride, img0);
         }
       }
     }
@@ -456,8 +472,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             v[g * 4 + 3] = fmaf(racc[ch * 32 + g * 4 + 3], sc.w, bi.w);
           }
           if (RES) {                   // residual slab was TMA-prefetched into shared memory (64 B swizzle)
-            if (ch == 0) mbar_wait(res_full_bar, tile_iter & 1u);
             const int sl = half * (HC / 32) + ch;
+            mbar_wait(&res_full_bar[sl], tile_iter & 1u);
             const int rsw = (row >> 1) & 3;
             const uint8_t* rh = res_stage + (sl * 2 + 0) * 8192 + row * 64;
             const uint8_t* rl = res_stage + (sl * 2 + 1) * 8192 + row * 64;
@@ -470,10 +486,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[g * 8 + j] += join_f16(ph[j], pl[j]);
             }
-            if (ch == HC / 32 - 1) {   // this warp is done with the residual tile
-              __syncwarp();
-              if (lane == 0) mbar_arrive(res_empty_bar);
-            }
+            __syncwarp();              // this warp is done with the slab
+            if (lane == 0) mbar_arrive(&res_empty_bar[sl]);
           } else if (a.res_hi && valid) {     // residual tensors always have cout % 32 == 0 channels
             const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + rpix * a.cout + c0);
             const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + rpix * a.cout + c0);
@@ -502,15 +516,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               }
             }
           } else {            // split outputs always have cout % 32 == 0
-            bool ovf = false;
+            // packed split: hi = rn16(v), lo = rn16(v - hi), two channels per cvt.rn.f16x2.f32; an fp16
+            // overflow shows up as inf/nan in the hi plane (tracked as a running |max| with NaN propagation)
             uint4 hv[4], lv[4];
-            __half* ph = reinterpret_cast<__half*>(hv);
-            __half* pl = reinterpret_cast<__half*>(lv);
+            __half2* ph = reinterpret_cast<__half2*>(hv);
+            __half2* pl = reinterpret_cast<__half2*>(lv);
+            __half2 amax = __float2half2_rn(0.f);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              ovf |= !(fabsf(v[j]) <= LUMI_F16_MAX);
-              split_f32(v[j], ph[j], pl[j]);
+            for (int j = 0; j < 16; ++j) {
+              split2_f32(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+              amax = __hmax2_nan(amax, __habs2(ph[j]));
             }
+            const uint32_t ab = *reinterpret_cast<const uint32_t*>(&amax);
+            const bool ovf = ((ab & 0x7C00u) == 0x7C00u) || ((ab & 0x7C000000u) == 0x7C000000u);
             if (ovf && valid && a.overflow) atomicOr(a.overflow, 1);
             if (store_leader) bulk_wait_group_read0();   // the previous slab's stores have drained the staging
             named_bar_sync(1 + half, 128);
@@ -700,7 +718,7 @@ static void launch_tc_cfg(const TcArgs& a, cudaStream_t st) {
   }
   const long total = (long)a.tiles_w * a.tiles_h * a.tiles_n * a.n_tiles;
   const int grid = (int)(total < sm_count() ? total : sm_count());     // persistent: one CTA per SM
-  conv_tc_kernel<BN, STAGES, RES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  conv_tc_kernel<BN, STAGES, RES><<<grid, RES ? TC_THREADS_RES : TC_THREADS, Cfg::SMEM_BYTES, st>>>(a);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
@@ -735,7 +753,7 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   a.n_tiles = L.cout_pad / bn;
   a.stride = L.stride;
   a.overflow = io.overflow_flag;
-  const bool res_tma = io.res.hi != nullptr && bn == 128 && !io.out_f32;
+  const bool res_tma = io.res.hi != nullptr && bn == 128 && L.cout % 128 == 0 && !io.out_f32;
   if (res_tma) {          // residual tile prefetched by TMA (box over the unit's input, subsampled by res_stride)
     a.tm_r_hi = cached_out_map(io.res.hi, io.res.n, io.res.h, io.res.w, io.res.c, nb, th, tw, io.res_stride);
     a.tm_r_lo = cached_out_map(io.res.lo, io.res.n, io.res.h, io.res.w, io.res.c, nb, th, tw, io.res_stride);

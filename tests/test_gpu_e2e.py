@@ -213,3 +213,27 @@ def test_engine_fails_loudly_on_missing_weight():
     with pytest.raises(ValueError):
         eng.set_weight(name, np.zeros((1, 1, 4, 4), np.float32))     # wrong shape
     eng.close()
+
+
+@pytest.mark.parametrize('impl', ['tc', 'simt'])
+def test_engine_reports_activation_overflow(impl):
+    """Activations travel as fp16 hi/lo planes; a layer output beyond the fp16 range must surface as
+    LUMI_EOVERFLOW (RuntimeError, code -5), never as silently wrong detections -- and the engine must
+    stay usable afterwards."""
+    cfg = frcnn_cfg('resnet_v1_50')
+    wts = synth.make_weights(cfg, seed=1)
+    big = dict(wts)
+    name = [n for n in wts if n.endswith('block1/unit_1/bottleneck_v1/conv1/weights')][0]
+    big[name] = wts[name] * np.float32(1e7)
+    imgs = synth.make_images(1, 96, 128, seed=5)
+    eng = Engine(cfg, max_batch=1, max_h=96, max_w=128)
+    eng.load_weights(big).finalize()
+    eng.set_conv_impl(impl)
+    with pytest.raises(RuntimeError, match='code -5'):
+        eng.predict_raw(imgs)
+    eng.close()
+    eng = Engine(cfg, max_batch=1, max_h=96, max_w=128)
+    eng.load_weights(wts).finalize()
+    eng.set_conv_impl(impl)
+    eng.predict_raw(imgs)           # sane weights: no overflow reported
+    eng.close()
