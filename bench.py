@@ -285,6 +285,7 @@ def run_ours(args, wl):
     for i in range(args.steps):
         eng.predict_device(imgs_dev[i % NROT], boxes, scores, labels, counts)
     prof = eng.profile_read()
+    layer_prof = eng.profile_read_layers()
     eng.profile(False)
 
     if rank == 0:
@@ -331,6 +332,10 @@ def run_ours(args, wl):
             'weight_bcast_ms': bcast_ms,
             'roofline': roof,
         }
+        if args.layers:      # per-conv-layer live timing (events around each launch, single stream, whole batch)
+            out['conv_layers'] = [{'layer': n, 'us': ms_ * 1e3 / c, 'gflop': w_ / c / 1e9,
+                                   'tflops': (w_ / c) / (ms_ / c * 1e-3) / 1e12 if ms_ > 0 else None}
+                                  for n, c, ms_, w_ in layer_prof]
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             if wts is None:
@@ -361,6 +366,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='frcnn_r50', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--layers', action='store_true', help='add a per-conv-layer timing table to the JSON line')
     ap.add_argument('--ncu-range', action='store_true',
                     help='run warm-up, then one step inside cudaProfilerStart/Stop (for ncu --profile-from-start off)')
     args = ap.parse_args()

@@ -78,10 +78,19 @@ int lumi_last_launch_count(lumi_engine* e);
  * (work = algorithmic FLOPs for conv_*, algorithmic bytes for roi_pool). */
 int lumi_profile_enable(lumi_engine* e, int enable);
 const char* lumi_profile_read(lumi_engine* e);
+/* Per-conv-layer detail of the spans drained by the last lumi_profile_read:
+ * "layer:spans:total_ms:flops;..." in execution order. */
+const char* lumi_profile_read_layers(lumi_engine* e);
 
 /* Choose the convolution implementation: 0 = fp32 SIMT implicit GEMM everywhere,
  * 1 = tcgen05 fp16x2-split tensor-core kernel wherever the layer qualifies (default). */
 int lumi_set_conv_impl(lumi_engine* e, int impl);
+
+/* Work scheduling of the tcgen05 convolution: 0 = whole output tiles only, 1 (default) = stream-K (the
+ * K loops of all tiles cut into equal per-SM ranges, partial tiles summed in a fixed order) for layers whose
+ * tile count would leave SMs idle in the last wave, 2 = stream-K wherever it is applicable. Results
+ * are deterministic in every mode; modes differ in fp32 summation order only. */
+int lumi_set_conv_streamk(lumi_engine* e, int mode);
 
 /* 1 (default): lumi_predict splits the batch in two halves that run on two streams, so the latency-bound
  * proposal / NMS kernels of one half overlap the convolutions of the other. 0: single stream. Results are
@@ -113,7 +122,8 @@ const char* lumi_op_last_error(void);      /* message of the last failed lumi_op
 /* conv2d NHWC fp32 in/out (converted to/from the fp16x2 split planes internally).
  * w: TF layout [kh,kw,cin,cout] fp32 on DEVICE.  scale/bias [cout] or NULL.
  * residual NHWC fp32 [n,ho,wo,cout] or NULL.  act: 0 none, 1 relu, 2 relu6.
- * padding: 0 VALID, 1 SAME, 2 explicit slim conv2d_same.  impl: 0 SIMT, 1 tcgen05. */
+ * padding: 0 VALID, 1 SAME, 2 explicit slim conv2d_same.  impl: 0 SIMT, 1 tcgen05
+ * (whole-tile schedule), 2 tcgen05 with the stream-K schedule forced. */
 int lumi_op_conv2d(const float* x, int n, int h, int w, int cin, const float* wgt, int kh, int kw, int cout,
                    int stride, int rate, int padding, const float* scale, const float* bias,
                    const float* residual, int act, int impl, float* y, int* ho, int* wo, void* stream);

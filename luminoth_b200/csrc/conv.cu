@@ -212,6 +212,45 @@ struct TcArgs {
   int n_tiles;                     // C_out tiles (cout_pad / BN)
   int stride;                      // TMA traversal stride of the activation map (1 or 2)
   int* overflow;
+  // stream-K (sk_mode != 0): the K loops of all tiles form one unit sequence that is cut into gridDim.x equal
+  // contiguous ranges; a CTA that starts in the middle of a tile writes its partial accumulators to
+  // sk_partials[blockIdx.x] and publishes sk_flags[blockIdx.x] = sk_epoch, the CTA holding the tile's first
+  // K iteration adds them (in CTA order -- deterministic) and runs the epilogue.
+  int sk_mode;
+  float* sk_partials;              // [gridDim.x][BN columns][128 rows] fp32
+  int* sk_flags;                   // [gridDim.x]
+  int sk_epoch;
+};
+
+// One unit of work of a persistent CTA: K iterations [k0, k1) of output tile `tile`.
+struct TcItem { int tile, k0, k1; };
+struct TcSched {
+  int mode, total_tiles, n_iters, t;
+  long long u, u_end;
+  __device__ TcSched(int mode_, int total_tiles_, int n_iters_) : mode(mode_), total_tiles(total_tiles_), n_iters(n_iters_) {
+    t = blockIdx.x;
+    const long long U = (long long)total_tiles * n_iters;
+    u = U * blockIdx.x / gridDim.x;
+    u_end = U * (blockIdx.x + 1) / gridDim.x;
+  }
+  __device__ static long long range_end(int cta, int total_tiles, int n_iters) {
+    return (long long)total_tiles * n_iters * (cta + 1) / gridDim.x;
+  }
+  __device__ bool next(TcItem& it) {
+    if (!mode) {                   // round robin over whole tiles
+      if (t >= total_tiles) return false;
+      it.tile = t; it.k0 = 0; it.k1 = n_iters;
+      t += gridDim.x;
+      return true;
+    }
+    if (u >= u_end) return false;
+    it.tile = (int)(u / n_iters);
+    it.k0 = (int)(u - (long long)it.tile * n_iters);
+    const long long rem = u_end - u;
+    it.k1 = (rem < (long long)(n_iters - it.k0)) ? it.k0 + (int)rem : n_iters;
+    u += it.k1 - it.k0;
+    return true;
+  }
 };
 
 constexpr int TC_A_BYTES = 128 * 128;       // 128 pixel rows x 64 fp16 (one 128 B swizzle row each)
@@ -289,31 +328,32 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
 
   const int cchunks = a.cin >> 6;
   const int n_iters = a.kh * a.kw * cchunks;
-  const int n_acc_chunks = (n_iters + TC_CHUNK_STAGES - 1) / TC_CHUNK_STAGES;
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer: one (tap, 64-channel) slice per stage
       const uint32_t stage_tx = 2u * (uint32_t)rows_valid * 128u + 2u * (uint32_t)Cfg::B_BYTES;
-      uint32_t git = 0, tile_iter = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+      uint32_t git = 0;
+      TcSched sched(a.sk_mode, total_tiles, n_iters);
+      TcItem item;
+      while (sched.next(item)) {
+        const int t = item.tile;
         const int nt = t % a.n_tiles, mt = t / a.n_tiles;
         const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
         const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
-        for (int tap = 0; tap < a.kh * a.kw; ++tap) {
+        for (int k = item.k0; k < item.k1; ++k, ++git) {
+          const int tap = k / cchunks, cc = k - tap * cchunks;
           const int r = tap / a.kw, s = tap % a.kw;
           const int iy = y0 * a.stride + r * a.rate - a.pad_t, ix = x0 * a.stride + s * a.rate - a.pad_l;
-          for (int cc = 0; cc < cchunks; ++cc, ++git) {
-            const uint32_t st = git % STAGES, ph = (git / STAGES) & 1u;
-            mbar_wait(&empty_bar[st], ph ^ 1u);
-            uint8_t* sbase = smem + st * Cfg::STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[st], stage_tx);
-            tma_load_4d(sbase, &a.tm_a_hi, &full_bar[st], cc * 64, ix, iy, img0);
-            tma_load_4d(sbase + TC_A_BYTES, &a.tm_a_lo, &full_bar[st], cc * 64, ix, iy, img0);
-            const int kcol = tap * a.cin + cc * 64;
-            tma_load_2d(sbase + 2 * TC_A_BYTES, &a.tm_b_hi, &full_bar[st], kcol, n0);
-            tma_load_2d(sbase + 2 * TC_A_BYTES + Cfg::B_BYTES, &a.tm_b_lo, &full_bar[st], kcol, n0);
-          }
+          const uint32_t st = git % STAGES, ph = (git / STAGES) & 1u;
+          mbar_wait(&empty_bar[st], ph ^ 1u);
+          uint8_t* sbase = smem + st * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[st], stage_tx);
+          tma_load_4d(sbase, &a.tm_a_hi, &full_bar[st], cc * 64, ix, iy, img0);
+          tma_load_4d(sbase + TC_A_BYTES, &a.tm_a_lo, &full_bar[st], cc * 64, ix, iy, img0);
+          const int kcol = tap * a.cin + cc * 64;
+          tma_load_2d(sbase + 2 * TC_A_BYTES, &a.tm_b_hi, &full_bar[st], kcol, n0);
+          tma_load_2d(sbase + 2 * TC_A_BYTES + Cfg::B_BYTES, &a.tm_b_lo, &full_bar[st], kcol, n0);
         }
       }
     }
@@ -322,14 +362,16 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
       // ---------------- MMA issuer: per K=16 slice  D1 += Ahi*Bhi ;  D2 += Ahi*Blo + Alo*Bhi
       constexpr uint32_t idesc = make_idesc_f16(128, BN);
       uint32_t git = 0, gchunk = 0, tile_iter = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+      TcSched sched(a.sk_mode, total_tiles, n_iters);
+      TcItem item;
+      for (; sched.next(item); ++tile_iter) {
         const uint32_t tbuf = tile_iter & 1u;
         mbar_wait(&d2_empty_bar[tbuf], ((tile_iter >> 1) & 1u) ^ 1u);     // previous user of D2[tbuf] drained
         tc_fence_after();
         const uint32_t d2 = tmem_base + (2u + tbuf) * BN;
         uint32_t d1 = 0, buf = 0;
-        for (int it = 0; it < n_iters; ++it, ++git) {
-          const int in_chunk = it % TC_CHUNK_STAGES;
+        for (int it = item.k0; it < item.k1; ++it, ++git) {
+          const int in_chunk = (it - item.k0) % TC_CHUNK_STAGES;
           if (in_chunk == 0) {
             buf = gchunk & 1u;
             mbar_wait(&acc_empty_bar[buf], ((gchunk >> 1) & 1u) ^ 1u);    // D1[buf] drained
@@ -348,11 +390,11 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
           for (int k = 0; k < 4; ++k) {
             const uint64_t ko = (uint64_t)(k * 2);      // 16 fp16 = 32 B = 2 x 16 B units
             umma_f16(d1, d_ahi + ko, d_bhi + ko, idesc, (in_chunk > 0 || k > 0) ? 1u : 0u);
-            umma_f16(d2, d_ahi + ko, d_blo + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_f16(d2, d_ahi + ko, d_blo + ko, idesc, (it > item.k0 || k > 0) ? 1u : 0u);
             umma_f16(d2, d_alo + ko, d_bhi + ko, idesc, 1u);
           }
           umma_commit(&empty_bar[st]);                  // frees the smem slot once these MMAs retire
-          if (in_chunk == TC_CHUNK_STAGES - 1 || it == n_iters - 1) {
+          if (in_chunk == TC_CHUNK_STAGES - 1 || it == item.k1 - 1) {
             umma_commit(&acc_full_bar[buf]);            // D1[buf] (and, on the last chunk, D2[tbuf]) complete
             ++gchunk;
           }
@@ -365,8 +407,12 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
       // plane) per barrier pair, refilled as soon as its four epilogue warps have read the previous tile's slab.
       // It runs on its own warp so that it never holds back the operand loads of the next tile.
       const uint32_t slab_tx = 2u * (uint32_t)rows_valid * 64u;
-      uint32_t tile_iter = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+      uint32_t tile_iter = 0;                       // counts the tiles whose epilogue runs in this CTA
+      TcSched sched(a.sk_mode, total_tiles, n_iters);
+      TcItem item;
+      while (sched.next(item)) {
+        if (item.k0 != 0) continue;                 // partial contribution: no epilogue here
+        const int t = item.tile;
         const int nt = t % a.n_tiles, mt = t / a.n_tiles;
         const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
         const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
@@ -381,6 +427,7 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
           tma_load_4d(res_stage + (sl * 2 + 1) * 8192, &a.tm_r_lo, &res_full_bar[sl], n0 + sl * 32,
                       x0 * a.res_stride, y0 * a.res_stride, img0);
         }
+        ++tile_iter;
       }
     }
   } else {
@@ -390,8 +437,12 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t gchunk = 0, tile_iter = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+    uint32_t gchunk = 0, tile_iter = 0, epi_iter = 0;
+    TcSched sched(a.sk_mode, total_tiles, n_iters);
+    TcItem item;
+    for (; sched.next(item); ++tile_iter) {
+      const int t = item.tile;
+      const int n_acc_chunks = (item.k1 - item.k0 + TC_CHUNK_STAGES - 1) / TC_CHUNK_STAGES;
       const int nt = t % a.n_tiles, mt = t / a.n_tiles;
       const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
       const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb;
@@ -448,6 +499,34 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
         if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
       }
 
+      // ---- stream-K fix-up
+      if (item.k0 != 0) {
+        // this CTA continued a tile somebody else started: publish the partial sums, no epilogue.  Layout
+        // [column][row] so that a warp (32 consecutive rows) writes 128 contiguous bytes per column.
+        float* wsp = a.sk_partials + (size_t)blockIdx.x * (128 * BN) + (size_t)(half * HC) * 128 + row;
+#pragma unroll
+        for (int j = 0; j < HC; ++j) wsp[j * 128] = racc[j];
+        __threadfence();
+        named_bar_sync(3, 256);                          // all 8 epilogue warps have written and fenced
+        if (warp == 2 && lane == 0)
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.sk_flags + blockIdx.x), "r"(a.sk_epoch) : "memory");
+        continue;
+      }
+      if (item.k1 != n_iters) {
+        // this CTA holds the head of the tile: the following CTAs hold the rest (they computed it first thing)
+        const long long tile_end = (long long)(t + 1) * n_iters;
+        for (int cta = blockIdx.x + 1;; ++cta) {
+          int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(a.sk_flags + cta) : "memory");
+          } while (seen != a.sk_epoch);
+          const float* wsp = a.sk_partials + (size_t)cta * (128 * BN) + (size_t)(half * HC) * 128 + row;
+#pragma unroll
+          for (int j = 0; j < HC; ++j) racc[j] = __fadd_rn(racc[j], __ldcg(wsp + j * 128));
+          if (TcSched::range_end(cta, total_tiles, n_iters) >= tile_end) break;
+        }
+      }
+
       // ---- scale/bias (folded BN) -> +residual -> activation -> store (overlaps the next tile's MMAs)
       // split outputs: each column half (4 warps) stages a 128 x 32-channel slab per plane in shared
       // memory (64 B swizzle) and one thread issues the two bulk tensor stores -- fully coalesced, and
@@ -473,7 +552,7 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
           }
           if (RES) {                   // residual slab was TMA-prefetched into shared memory (64 B swizzle)
             const int sl = half * (HC / 32) + ch;
-            mbar_wait(&res_full_bar[sl], tile_iter & 1u);
+            mbar_wait(&res_full_bar[sl], epi_iter & 1u);
             const int rsw = (row >> 1) & 3;
             const uint8_t* rh = res_stage + (sl * 2 + 0) * 8192 + row * 64;
             const uint8_t* rl = res_stage + (sl * 2 + 1) * 8192 + row * 64;
@@ -548,6 +627,7 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
           }
         }
       }
+      ++epi_iter;
     }
     if (((warp - 2) & 3) == 0 && lane == 0) bulk_wait_group0();   // all output stores complete before exit
   }
@@ -707,8 +787,25 @@ static int sm_count() {
   return (r > 0 && r < n) ? n - r : n;
 }
 
+int g_conv_streamk = 1;            // 0 off, 1 auto (wave-quantisation heuristic), 2 whenever possible
+
+void conv_workspace_create(ConvWorkspace& w) {
+  int dev = 0, n = 0;
+  LUMI_CUDA_CHECK(cudaGetDevice(&dev));
+  LUMI_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  w.ctas = n;
+  LUMI_CUDA_CHECK(cudaMalloc(&w.partials, (size_t)n * 128 * 128 * sizeof(float)));
+  LUMI_CUDA_CHECK(cudaMalloc(&w.flags, (size_t)n * sizeof(int)));
+  LUMI_CUDA_CHECK(cudaMemset(w.flags, 0, (size_t)n * sizeof(int)));
+  w.epoch = 0;
+}
+void conv_workspace_free(ConvWorkspace& w) {
+  cudaFree(w.partials); cudaFree(w.flags);
+  w.partials = nullptr; w.flags = nullptr; w.ctas = 0;
+}
+
 template <int BN, int STAGES, bool RES>
-static void launch_tc_cfg(const TcArgs& a, cudaStream_t st) {
+static void launch_tc_cfg(const TcArgs& a, ConvWorkspace* sk, cudaStream_t st) {
   using Cfg = TcCfg<BN, STAGES, RES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -717,8 +814,29 @@ static void launch_tc_cfg(const TcArgs& a, cudaStream_t st) {
     attr_set = true;
   }
   const long total = (long)a.tiles_w * a.tiles_h * a.tiles_n * a.n_tiles;
-  const int grid = (int)(total < sm_count() ? total : sm_count());     // persistent: one CTA per SM
-  conv_tc_kernel<BN, STAGES, RES><<<grid, RES ? TC_THREADS_RES : TC_THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  const int sms = sm_count();
+  int grid = (int)(total < sms ? total : sms);                          // persistent: one CTA per SM
+  TcArgs args = a;
+  args.sk_mode = 0;
+  if (sk && sk->partials && g_conv_streamk > 0 && sms <= sk->ctas) {
+    // stream-K when whole-tile scheduling would leave SMs idle in the last wave (or has fewer tiles than SMs).
+    // It balances K iterations, not epilogues, and every CTA pays one partial-tile write and one read: measured
+    // (profiles/r1_streamk_per_layer.txt) it wins 13-26 % on the long-K layers (3x3 with C_in >= 128,
+    // 1x1 with C_in >= 1024, the RPN conv) and loses 5-35 % on short-K, epilogue-bound ones -- hence the K floor.
+    const long n_iters = (long)a.kh * a.kw * (a.cin >> 6);
+    const double waves = (double)total / sms;
+    const double eff = waves / std::ceil(waves);
+    const long units_per_cta = total * n_iters / sms;
+    const bool forced = g_conv_streamk >= 2 && units_per_cta >= 3;
+    if (forced || (eff < 0.92 && n_iters >= 12 && units_per_cta >= 12)) {
+      args.sk_mode = 1;
+      args.sk_partials = sk->partials;
+      args.sk_flags = sk->flags;
+      args.sk_epoch = (int)(++sk->epoch & 0x7fffffff);
+      grid = sms;
+    }
+  }
+  conv_tc_kernel<BN, STAGES, RES><<<grid, RES ? TC_THREADS_RES : TC_THREADS, Cfg::SMEM_BYTES, st>>>(args);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
@@ -757,11 +875,11 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   if (res_tma) {          // residual tile prefetched by TMA (box over the unit's input, subsampled by res_stride)
     a.tm_r_hi = cached_out_map(io.res.hi, io.res.n, io.res.h, io.res.w, io.res.c, nb, th, tw, io.res_stride);
     a.tm_r_lo = cached_out_map(io.res.lo, io.res.n, io.res.h, io.res.w, io.res.c, nb, th, tw, io.res_stride);
-    launch_tc_cfg<128, 2, true>(a, st);
+    launch_tc_cfg<128, 2, true>(a, io.sk, st);
   } else if (bn == 128) {
-    launch_tc_cfg<128, 3, false>(a, st);
+    launch_tc_cfg<128, 3, false>(a, io.sk, st);
   } else {
-    launch_tc_cfg<64, 4, false>(a, st);
+    launch_tc_cfg<64, 4, false>(a, io.sk, st);
   }
 }
 

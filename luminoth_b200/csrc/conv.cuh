@@ -22,6 +22,18 @@ struct ConvLayer {
   bool tc_ready = false;
 };
 
+// Scratch of the stream-K schedule (see conv.cu): one partial-accumulator slot + flag per persistent CTA.
+// One workspace per stream: launches that share it must be stream-ordered.
+struct ConvWorkspace {
+  float* partials = nullptr;
+  int* flags = nullptr;
+  unsigned epoch = 0;
+  int ctas = 0;
+};
+void conv_workspace_create(ConvWorkspace& w);
+void conv_workspace_free(ConvWorkspace& w);
+extern int g_conv_streamk;        // 0 off, 1 auto (default), 2 whenever possible
+
 struct ConvIO {
   Act in;
   Act out;                  // split-plane output (used when out_f32 == nullptr)
@@ -31,6 +43,7 @@ struct ConvIO {
   int pad_t = 0, pad_l = 0;
   int ho = 0, wo = 0;
   int* overflow_flag = nullptr;
+  ConvWorkspace* sk = nullptr;  // enables stream-K scheduling on the tcgen05 path (nullptr: whole tiles only)
   // Optional strided ("Toeplitz") view of the input for the tcgen05 path: element pitches between
   // consecutive pixels / rows / images (0 = dense NHWC).  Used by the space-to-depth stem, where each
   // A row is the 64 contiguous fp16 of four horizontally adjacent 16-channel pixels.

@@ -15,6 +15,7 @@
 #include "json.hpp"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -111,6 +112,8 @@ struct lumi_engine {
   int pipeline = 1;             // 1: split the batch in two and run the halves on two streams (hides the
                                 // latency-bound proposal / NMS kernels of one half under the other half's convs)
   int* d_overflow = nullptr;
+  ConvWorkspace sk_ws[2];       // stream-K scratch, one per stream
+  int conv_streamk = 1;         // 0 off, 1 auto, 2 whenever possible
   uint8_t* d_images = nullptr; size_t images_cap = 0;
   float* d_boxes = nullptr; float* d_scores = nullptr; int* d_labels = nullptr; int* d_counts = nullptr;
   int* d_prop_counts = nullptr;
@@ -118,15 +121,16 @@ struct lumi_engine {
   int planned_n = 0, planned_h = 0, planned_w = 0;
   // per-category device timing (CUDA events on the engine stream), for bench.py's roofline
   bool profile = false;
-  struct ProfSpan { int cat; cudaEvent_t a, b; double work; };
+  struct ProfSpan { int cat; cudaEvent_t a, b; double work; std::string label; };
   std::vector<ProfSpan> prof_spans;
   std::vector<cudaEvent_t> prof_pool;
-  std::string prof_text;
+  std::string prof_text, prof_layers_text;
 
   ~lumi_engine() {
     for (auto& kv : layers) conv_layer_free(kv.second);
     for (auto& kv : dev_vecs) cudaFree(kv.second);
     nms_workspace_free(ws_rpn); nms_workspace_free(ws_det);
+    conv_workspace_free(sk_ws[0]); conv_workspace_free(sk_ws[1]);
     cudaFree(d_anchor_ref); cudaFree(d_anchors); cudaFree(d_final_keys); cudaFree(d_ssd_anchors);
     cudaFree(arena.base); cudaFree(arena2.base); cudaFree(d_final_keys2); cudaFree(d_overflow); cudaFree(d_images);
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -497,9 +501,9 @@ cudaEvent_t prof_event(lumi_engine* e) {
 struct ProfScope {
   lumi_engine* e; int idx = -1;
   // work: algorithmic FLOPs (conv) or bytes (HBM-bound stages) of the kernels inside the span
-  ProfScope(lumi_engine* eng, bool dry, int cat, double work = 0.0) : e(eng) {
+  ProfScope(lumi_engine* eng, bool dry, int cat, double work = 0.0, const std::string& label = std::string()) : e(eng) {
     if (dry || !e->profile) return;
-    lumi_engine::ProfSpan sp{cat, prof_event(e), prof_event(e), work};
+    lumi_engine::ProfSpan sp{cat, prof_event(e), prof_event(e), work, label};
     LUMI_CUDA_CHECK(cudaEventRecord(sp.a, e->stream));
     e->prof_spans.push_back(sp);
     idx = (int)e->prof_spans.size() - 1;
@@ -515,6 +519,7 @@ struct Ctx {
   Arena* arena = nullptr;       // workspace of this (half-)batch
   int img_off = 0;              // first image of this (half-)batch inside the engine-level batch buffers
   float* final_keys = nullptr;  // scratch of the final top-k sort
+  ConvWorkspace* sk = nullptr;  // stream-K scratch of this stream
   bool taps = true;             // record debug taps (first half only)
   Act act(int n, int h, int w, int c) {
     Act a; a.n = n; a.h = h; a.w = w; a.c = c;
@@ -592,12 +597,13 @@ Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* re
   if (res) { io.res = *res; io.res_stride = res_stride; }
   if (view_pitch) { io.in_pix_pitch = view_pitch[0]; io.in_row_pitch = view_pitch[1]; io.in_img_pitch = view_pitch[2]; }
   io.overflow_flag = cx.e->d_overflow;
+  io.sk = cx.sk;
   if (!cx.dry) {
     const bool tc = cx.e->conv_impl == 1 && conv_tc_supported(L, io);
     const double flops = algorithmic_flops >= 0 ? algorithmic_flops
                                                 : 2.0 * (double)in.n * ho * wo * (double)L.kh * L.kw * L.cin * L.cout;
     LUMI_REQUIRE(tc || !view_pitch, "strided input views exist only on the tcgen05 path (internal)");
-    ProfScope ps(cx.e, cx.dry, tc ? PC_CONV_TC : PC_CONV_SIMT, flops);
+    ProfScope ps(cx.e, cx.dry, tc ? PC_CONV_TC : PC_CONV_SIMT, flops, key);
     if (tc) launch_conv_tc(L, io, cx.st);
     else launch_conv_simt(L, io, cx.st);
   }
@@ -911,6 +917,7 @@ Ctx make_ctx(lumi_engine* e, bool dry, int half) {
   cx.st = half ? e->stream2 : e->stream;
   cx.arena = half ? &e->arena2 : &e->arena;
   cx.final_keys = half ? e->d_final_keys2 : e->d_final_keys;
+  cx.sk = &e->sk_ws[half ? 1 : 0];
   cx.taps = half == 0;
   return cx;
 }
@@ -1049,7 +1056,10 @@ int lumi_finalize(lumi_engine* e) {
     nms_workspace_alloc(e->ws_det, nb * e->num_classes, e->ssd_total_anchors, e->det.class_max);
     LUMI_CUDA_CHECK(cudaMalloc(&e->d_final_keys, det_final_scratch_bytes(nb, e->num_classes, e->det.class_max)));
   }
+  conv_workspace_create(e->sk_ws[0]);
+  if (const char* v = std::getenv("LUMI_CONV_STREAMK")) e->conv_streamk = std::max(0, std::min(2, std::atoi(v)));
   if (e->max_batch >= 2) {
+    conv_workspace_create(e->sk_ws[1]);
     LUMI_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
     LUMI_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     LUMI_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
@@ -1099,6 +1109,7 @@ int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n
   if (e->type == "fasterrcnn") ensure_frcnn_anchors(e, h, w, e->stream);
   Ctx cx = make_ctx(e, false, 0);
   g_conv_sm_reserve = piped ? 8 : 0;
+  g_conv_streamk = e->conv_streamk;
   if (piped) {
     LUMI_CUDA_CHECK(cudaEventRecord(e->ev_fork, e->stream));
     LUMI_CUDA_CHECK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
@@ -1181,6 +1192,12 @@ int lumi_set_conv_impl(lumi_engine* e, int impl) {
   return LUMI_OK;
 }
 
+int lumi_set_conv_streamk(lumi_engine* e, int mode) {
+  if (!e || mode < 0 || mode > 2) return LUMI_EINVAL;
+  e->conv_streamk = mode;
+  return LUMI_OK;
+}
+
 int lumi_profile_enable(lumi_engine* e, int enable) {
   if (!e) return LUMI_EINVAL;
   e->profile = enable != 0;
@@ -1196,12 +1213,26 @@ const char* lumi_profile_read(lumi_engine* e) {
     LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     double ms[PC_COUNT] = {0}, work[PC_COUNT] = {0};
     int cnt[PC_COUNT] = {0};
+    std::map<std::string, std::array<double, 3>> per_layer;     // label -> {spans, ms, work}
+    std::vector<std::string> order;
     for (auto& sp : e->prof_spans) {
       float t = 0.f;
-      if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) { ms[sp.cat] += t; cnt[sp.cat]++; work[sp.cat] += sp.work; }
+      if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) {
+        ms[sp.cat] += t; cnt[sp.cat]++; work[sp.cat] += sp.work;
+        if (!sp.label.empty()) {
+          auto it = per_layer.find(sp.label);
+          if (it == per_layer.end()) { it = per_layer.emplace(sp.label, std::array<double, 3>{0, 0, 0}).first; order.push_back(sp.label); }
+          it->second[0] += 1; it->second[1] += t; it->second[2] += sp.work;
+        }
+      }
       e->prof_pool.push_back(sp.a); e->prof_pool.push_back(sp.b);
     }
     e->prof_spans.clear();
+    e->prof_layers_text.clear();
+    for (const std::string& k : order) {
+      const auto& v = per_layer[k];
+      e->prof_layers_text += k + ":" + std::to_string((long)v[0]) + ":" + std::to_string(v[1]) + ":" + std::to_string(v[2]) + ";";
+    }
     e->prof_text.clear();
     for (int c = 0; c < PC_COUNT; ++c)
       e->prof_text += std::string(PROF_NAMES[c]) + ":" + std::to_string(cnt[c]) + ":" + std::to_string(ms[c]) + ":" +
@@ -1209,6 +1240,10 @@ const char* lumi_profile_read(lumi_engine* e) {
   } catch (const Error& err) { e->last_error = err.what(); return ""; }
   return e->prof_text.c_str();
 }
+
+// Per-conv-layer breakdown of the spans drained by the LAST lumi_profile_read: "layer:spans:total_ms:flops;..."
+// in execution order.
+const char* lumi_profile_read_layers(lumi_engine* e) { return e ? e->prof_layers_text.c_str() : ""; }
 
 int lumi_get_tensor(lumi_engine* e, const char* name, float* out, int64_t capacity, int64_t* numel, int64_t* shape4) {
   if (!e) return LUMI_EINVAL;

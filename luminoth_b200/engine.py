@@ -43,10 +43,12 @@ SIGNATURES = {
     'lumi_synchronize': (ctypes.c_int, [ctypes.c_void_p]),
     'lumi_last_launch_count': (ctypes.c_int, [ctypes.c_void_p]),
     'lumi_set_conv_impl': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    'lumi_set_conv_streamk': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'lumi_set_debug_taps': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'lumi_set_pipeline': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'lumi_profile_enable': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'lumi_profile_read': (ctypes.c_char_p, [ctypes.c_void_p]),
+    'lumi_profile_read_layers': (ctypes.c_char_p, [ctypes.c_void_p]),
     'lumi_get_tensor': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, _c_i64_p,
                                        _c_i64_p]),
     'lumi_last_error': (ctypes.c_char_p, [ctypes.c_void_p]),
@@ -173,6 +175,12 @@ class Engine(object):
         if rc != LUMI_OK:
             raise ValueError('conv impl must be "simt" or "tc"')
 
+    def set_conv_streamk(self, mode):
+        """tcgen05 conv scheduling: 'off' (whole tiles), 'auto' (default), 'always' (stream-K wherever applicable)."""
+        rc = self._lib.lumi_set_conv_streamk(self._h, {'off': 0, 'auto': 1, 'always': 2}.get(mode, mode))
+        if rc != LUMI_OK:
+            raise ValueError('stream-K mode must be "off", "auto" or "always"')
+
     # ---- forward
     def predict_raw(self, images):
         """images: uint8 array [n,h,w,3] (numpy -> host path, H2D inside the
@@ -232,6 +240,16 @@ class Engine(object):
             if part:
                 name, cnt, ms, work = part.split(':')
                 out[name] = (int(cnt), float(ms), float(work))
+        return out
+
+    def profile_read_layers(self):
+        """[(conv layer, spans, total_ms, flops)] of the spans drained by the last profile_read()."""
+        txt = self._lib.lumi_profile_read_layers(self._h).decode()
+        out = []
+        for part in txt.split(';'):
+            if part:
+                name, cnt, ms, work = part.rsplit(':', 3)
+                out.append((name, int(cnt), float(ms), float(work)))
         return out
 
     def synchronize(self):

@@ -65,14 +65,17 @@ CONV_CASES = [
     ('roi_7x7', 5, 7, 7, 128, 128, 3, 1, 1, 'SAME', True, 1),
     ('wide_256', 1, 38, 64, 256, 256, 3, 1, 1, 'SAME', False, 1),
     ('1x1_1024_256', 1, 38, 64, 1024, 256, 1, 1, 1, 'SAME', False, 1),
+    # enough tiles that a stream-K range holds whole tiles plus a head and a tail piece
+    ('sk_many_tiles', 2, 64, 96, 128, 256, 3, 1, 1, 'SAME', True, 1),
+    ('sk_1x1_512_128', 3, 40, 64, 512, 128, 1, 1, 1, 'SAME', False, 1),
 ]
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc_streamk'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv2d_matches_oracle(case, impl):
     name, n, h, w, cin, cout, k, stride, rate, padding, use_res, act = case
-    if impl == 'tc' and cin % 64 != 0:
+    if impl != 'simt' and cin % 64 != 0:
         pytest.skip('layer shape runs on the SIMT kernel by design')
     import zlib
     rng = np.random.default_rng(zlib.crc32(name.encode()))
