@@ -174,7 +174,7 @@ def run_ours(args, wl):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     cfg = build_config(wl)
-    B, H, W = wl['batch'], wl['h'], wl['w']
+    B, H, W = (args.per_gpu_batch or wl['batch']), wl['h'], wl['w']
 
     # ---- weights: rank 0 owns them, NCCL broadcast to the other GPUs (once, outside the step)
     eng = Engine(cfg, device=local, max_batch=B, max_h=H, max_w=W)
@@ -319,7 +319,8 @@ def run_ours(args, wl):
             'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32 (fp16x2-split operands on tcgen05 kind::f16, fp32 accumulate)',
             'data': 'synthetic',
-            'config': {'workload': wl['name'], 'global_batch': total_imgs, 'per_gpu_batch': B,
+            'config': {'workload': wl['name'] + (' [batch overridden to %d]' % B if args.per_gpu_batch else ''),
+                       'global_batch': total_imgs, 'per_gpu_batch': B,
                        'parallelism': 'dp%d (images sharded, NCCL weight broadcast + detection all-gather)' % world,
                        'l2': 'inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); per-step activation '
                              'working set is several GB' % (NROT, NROT * B * H * W * 3 / 1e6),
@@ -366,6 +367,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='frcnn_r50', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--per-gpu-batch', type=int, default=0,
+                    help='override the workload batch (latency studies; the headline number uses the default)')
     ap.add_argument('--layers', action='store_true', help='add a per-conv-layer timing table to the JSON line')
     ap.add_argument('--ncu-range', action='store_true',
                     help='run warm-up, then one step inside cudaProfilerStart/Stop (for ncu --profile-from-start off)')

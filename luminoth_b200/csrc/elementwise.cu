@@ -64,6 +64,37 @@ void launch_stem_s2d(const uint8_t* img, int n, int h, int w, Act x2, const floa
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
 
+// SSD conv1_1 (3x3, C_in = 3) staging for the tensor-core path: zero-padded image with 16-channel
+// pixels (3 real), so that the 64 contiguous fp16 starting at pixel (y, x) are the filter-row window
+// x-1 .. x+2 of row y-1 (the 4th pixel meets zero weights).  uint8 values are exact in fp16: lo = 0.
+__global__ void pack_c3_kernel(const uint8_t* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo, int n,
+                               int h, int w, int h2, int w2) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)n * h2 * w2;
+  if (i >= total) return;
+  const int X = (int)(i % w2), Y = (int)((i / w2) % h2), ni = (int)(i / ((size_t)w2 * h2));
+  uint4 vh[2];
+  __half* ph = reinterpret_cast<__half*>(vh);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) ph[j] = __float2half_rn(0.f);
+  const int py = Y - 1, px = X - 1;
+  if (py >= 0 && py < h && px >= 0 && px < w) {
+    const uint8_t* p = img + (((size_t)ni * h + py) * w + px) * 3;
+    ph[0] = __float2half_rn((float)p[0]); ph[1] = __float2half_rn((float)p[1]); ph[2] = __float2half_rn((float)p[2]);
+  }
+  uint4* oh = reinterpret_cast<uint4*>(hi + i * 16);
+  uint4* ol = reinterpret_cast<uint4*>(lo + i * 16);
+  oh[0] = vh[0]; oh[1] = vh[1];
+  ol[0] = make_uint4(0u, 0u, 0u, 0u); ol[1] = make_uint4(0u, 0u, 0u, 0u);
+}
+void launch_pack_c3(const uint8_t* img, int n, int h, int w, Act x2, cudaStream_t st) {
+  size_t total = (size_t)n * x2.h * x2.w;
+  if (!total) return;
+  pack_c3_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(img, x2.hi, x2.lo, n, h, w, x2.h, x2.w);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
 __global__ void f32_to_act_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
                                   size_t numel) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -468,6 +468,24 @@ void build_layers(lumi_engine* e) {
         const std::string p = s + "/vgg_16/" + VGG_NAMES[b] + "/" + VGG_NAMES[b] + "_" + std::to_string(r + 1);
         make_conv_bias(e, p, {p + "/weights"}, {p + "/biases"}, 1, 1, ACT_RELU);
       }
+    {   // tcgen05 form of conv1_1 (3x3 over 3 channels): one filter row = 4 pixels x 16 ch = one K=64 slice
+        // (kh=3, kw=1, cin=64) over the padded 16-channel staging written by launch_pack_c3
+      const std::string p = s + "/vgg_16/conv1/conv1_1";
+      const HostTensor& w = W(e, p + "/weights");
+      const HostTensor& b = W(e, p + "/biases");
+      const int co_n = (int)w.shape[3];
+      LUMI_REQUIRE(w.shape[0] == 3 && w.shape[1] == 3 && w.shape[2] == 3, "conv1_1 must be 3x3x3");
+      std::vector<float> w2((size_t)3 * 64 * co_n, 0.f);
+      for (int r = 0; r < 3; ++r)
+        for (int sx = 0; sx < 3; ++sx)
+          for (int c = 0; c < 3; ++c)
+            for (int co = 0; co < co_n; ++co)
+              w2[((size_t)r * 64 + sx * 16 + c) * co_n + co] = w.v[(((size_t)r * 3 + sx) * 3 + c) * co_n + co];
+      ConvLayer L;
+      L.kh = 3; L.kw = 1; L.cin = 64; L.cout = co_n; L.stride = 1; L.rate = 1; L.act = ACT_RELU;
+      conv_layer_upload(L, w2.data(), nullptr, b.v.data());
+      e->layers[p + "#pack"] = L;
+    }
     {
       const HostTensor& g = W(e, s + "/conv_4_3_norm/gamma");
       float* d = nullptr;
@@ -847,11 +865,23 @@ void forward_ssd(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   lumi_engine* e = cx.e;
   LUMI_REQUIRE(h == e->fixed_h && w == e->fixed_w, "SSD expects images of the configured fixed size");
   const std::string s = "ssd/ssd_feature_extractor";
-  Act x = cx.act(n, h, w, 3);
-  if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_u8_to_act(images, x, nullptr, cx.st); }  // no mean subtraction (quirk Q7)
+  Act x;
+  const bool c11_tc = e->conv_impl == 1;
+  if (c11_tc) {
+    // conv1_1 on the tensor cores: zero-padded 16-channel staging, Toeplitz view, 3 filter rows of K=64
+    Act x2 = cx.act(n, h + 2, w + 3, 16);
+    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_pack_c3(images, n, h, w, x2, cx.st); }   // no mean subtraction (quirk Q7)
+    Act view = x2;
+    view.w = w; view.c = 64;
+    const long pitch[3] = {16, (long)(w + 3) * 16, (long)(h + 2) * (w + 3) * 16};
+    x = run_conv(cx, s + "/vgg_16/conv1/conv1_1#pack", view, 0, nullptr, 1, nullptr, pitch, 2.0 * n * h * w * 27.0 * 64.0);
+  } else {
+    x = cx.act(n, h, w, 3);
+    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_u8_to_act(images, x, nullptr, cx.st); }  // no mean subtraction (quirk Q7)
+  }
   Act fmaps[6];
   for (int b = 0; b < 5; ++b) {
-    for (int r = 0; r < VGG_REPS[b]; ++r)
+    for (int r = (b == 0 && c11_tc) ? 1 : 0; r < VGG_REPS[b]; ++r)
       x = run_conv(cx, s + "/vgg_16/" + VGG_NAMES[b] + "/" + VGG_NAMES[b] + "_" + std::to_string(r + 1), x, 1, nullptr,
                    1, nullptr);
     if (b == 3) {                                                         // conv4_3 -> l2norm x gamma

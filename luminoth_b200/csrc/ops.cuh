@@ -9,6 +9,7 @@ void launch_u8_to_act(const uint8_t* img, Act out, const float* means /*3 or nul
 void launch_f32_to_act(const float* x, Act out, cudaStream_t st);
 // x2: (n, Ho+3, Wo+3, 16) space-to-depth staging of the 7x7/2 stem input (see elementwise.cu)
 void launch_stem_s2d(const uint8_t* img, int n, int h, int w, Act x2, const float* means, cudaStream_t st);
+void launch_pack_c3(const uint8_t* img, int n, int h, int w, Act x2 /*(n,h+2,w+3,16)*/, cudaStream_t st);
 void launch_act_to_f32(Act in, float* y, cudaStream_t st);
 void launch_max_pool(Act in, Act out, int k, int stride, int pad_t, int pad_l, cudaStream_t st);
 void launch_l2norm_scale(Act in, Act out, const float* gamma, float eps, cudaStream_t st);

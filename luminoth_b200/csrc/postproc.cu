@@ -329,23 +329,42 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
     unsigned long long bits = 0ull;
     if (thr > 0.f) {
       const NBox ni = normalise_box(bi);
-      uint32_t lo = 0u, hi = 0u;
+      uint32_t lo = 0u, hi = 0u, alo = 0u, ahi = 0u;
       if (ni.area > 0.f) {
+        // branch-free: `lo/hi` collect the pairs that are certainly above the threshold (ratio > thr (1 + 2^-20)),
+        // `alo/ahi` the ones inside the +-2^-20 margin; only those (practically never) take the exact IEEE divide
+        // afterwards.  The sign of fma(-t, union, inter) is the sign of the exact difference.
         const float thr_hi = __fmul_rn(thr, 1.00000095f), thr_lo = __fmul_rn(thr, 0.99999905f);
-#pragma unroll 16
-        for (int j = 0; j < 64; ++j) {
-          const float4 c = cmm[j];
-          const float ca = carea[j];                           // +inf for columns that can never suppress
-          const float dx = __fsub_rn(fminf(ni.xmax, c.z), fmaxf(ni.xmin, c.x));
-          const float dy = __fsub_rn(fminf(ni.ymax, c.w), fmaxf(ni.ymin, c.y));
-          const float inter = __fmul_rn(fmaxf(dy, 0.f), fmaxf(dx, 0.f));
-          const float uni = __fsub_rn(__fadd_rn(ni.area, ca), inter);
-          bool pred = inter > __fmul_rn(thr_hi, uni);          // ratio > thr (1 + 2^-21): certainly suppressed
-          if (!pred && inter >= __fmul_rn(thr_lo, uni)) pred = iou_exact_gt(inter, uni, thr);   // within the margin
-          if (j < 32) lo |= (uint32_t)pred << j; else hi |= (uint32_t)pred << (j - 32);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t s_bits = 0u, m_bits = 0u;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = h * 32 + jj;
+            const float4 c = cmm[j];
+            const float ca = carea[j];                         // +inf for columns that can never suppress
+            const float dx = __fsub_rn(fminf(ni.xmax, c.z), fmaxf(ni.xmin, c.x));
+            const float dy = __fsub_rn(fminf(ni.ymax, c.w), fmaxf(ni.ymin, c.y));
+            const float inter = __fmul_rn(fmaxf(dy, 0.f), fmaxf(dx, 0.f));
+            const float uni = __fsub_rn(__fadd_rn(ni.area, ca), inter);
+            if (fmaf(-thr_hi, uni, inter) > 0.f) s_bits |= 1u << jj;
+            if (fmaf(-thr_lo, uni, inter) >= 0.f) m_bits |= 1u << jj;   // includes the sure ones; NaN -> false
+          }
+          if (h == 0) { lo = s_bits; alo = m_bits; } else { hi = s_bits; ahi = m_bits; }
         }
       }
       bits = ((unsigned long long)hi << 32) | lo;
+      unsigned long long amb = (((unsigned long long)ahi << 32) | alo) & ~bits;
+      while (amb) {                                             // ratios within 2^-20 of the threshold
+        const int j = __ffsll((long long)amb) - 1;
+        amb &= amb - 1ull;
+        const float4 c = cmm[j];
+        const float dx = __fsub_rn(fminf(ni.xmax, c.z), fmaxf(ni.xmin, c.x));
+        const float dy = __fsub_rn(fminf(ni.ymax, c.w), fmaxf(ni.ymin, c.y));
+        const float inter = __fmul_rn(fmaxf(dy, 0.f), fmaxf(dx, 0.f));
+        const float uni = __fsub_rn(__fadd_rn(ni.area, carea[j]), inter);
+        if (iou_exact_gt(inter, uni, thr)) bits |= 1ull << j;
+      }
       if (cb == rb) bits &= ~((2ull << t) - 1ull);            // only columns > i
     } else {                                                  // thr <= 0: generic exact path
       const int jmax = min(64, n - cb * 64);
