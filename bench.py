@@ -255,7 +255,11 @@ def run_ours(args, wl):
         return float(ms.item())
 
     if args.ncu_range:
-        # evidence mode for `ncu --profile-from-start off`: warm up, then expose exactly ONE step to the profiler
+        # evidence mode for `ncu --profile-from-start off`: warm up, then expose exactly ONE step to the profiler.
+        # --ncu-unpiped: single stream, whole batch per launch -- the configuration of the per-category event
+        # profile that `roofline.achieved` comes from (ncu serialises kernels anyway)
+        if args.ncu_unpiped:
+            eng.set_pipeline(False)
         for i in range(args.warmup):
             step_device(i)
         eng.synchronize()
@@ -370,6 +374,7 @@ def main():
     ap.add_argument('--per-gpu-batch', type=int, default=0,
                     help='override the workload batch (latency studies; the headline number uses the default)')
     ap.add_argument('--layers', action='store_true', help='add a per-conv-layer timing table to the JSON line')
+    ap.add_argument('--ncu-unpiped', action='store_true', help='with --ncu-range: single-stream forward')
     ap.add_argument('--ncu-range', action='store_true',
                     help='run warm-up, then one step inside cudaProfilerStart/Stop (for ncu --profile-from-start off)')
     args = ap.parse_args()
