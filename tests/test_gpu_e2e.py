@@ -287,3 +287,28 @@ def test_stream_k_schedule_is_result_neutral():
         k = int(c0[i])
         assert box_dev(b1[i, :k], l1[i, :k], b0[i, :k], l0[i, :k]) <= 2e-3
     eng.close()
+
+
+def test_engine_capacity_is_not_part_of_the_result():
+    """An engine created for (max_batch 4, 256x384) must give, for a smaller batch of smaller images, exactly
+    what a tightly sized engine gives (ragged use of one handle: predicting.py serves images of any size);
+    an image beyond the planned maximum is refused, not truncated."""
+    cfg = frcnn_cfg('resnet_v1_50')
+    wts = synth.make_weights(cfg, seed=7)
+    imgs = synth.make_images(1, 160, 224, seed=8)
+    big = Engine(cfg, max_batch=4, max_h=256, max_w=384)
+    big.load_weights(wts).finalize()
+    tight = Engine(cfg, max_batch=1, max_h=160, max_w=224)
+    tight.load_weights(wts).finalize()
+    a = big.predict_raw(imgs)
+    b = tight.predict_raw(imgs)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x[:1], y[:1])
+    # a different size on the same handle afterwards, then the first size again: no state leaks between calls
+    other = synth.make_images(2, 192, 256, seed=9)
+    big.predict_raw(other)
+    for x, y in zip(big.predict_raw(imgs), a):
+        np.testing.assert_array_equal(x, y)
+    with pytest.raises((ValueError, RuntimeError)):
+        big.predict_raw(synth.make_images(1, 300, 400, seed=1))        # larger than the planned maximum
+    big.close(); tight.close()

@@ -165,6 +165,31 @@ def test_nms_bitmask_identical_keep_set(n, thr, max_out):
     np.testing.assert_array_equal(got, ref)
 
 
+def test_nms_ratio_exactly_at_threshold_takes_the_exact_path():
+    """IoU == threshold is NOT suppressed (tf.image.non_max_suppression uses a strict >).  The mask kernel decides
+    almost every pair with a +-2^-20 margin test and only divides inside the margin: these pairs sit exactly on
+    it, one ulp below it and one ulp above it."""
+    a = [0, 0, 2, 2]; b = [0, 0, 2, 1]                       # inter 2, union 4 -> IoU 0.5 exactly
+    c = [10, 10, 12, 11]; d = [11, 10, 13, 11]               # inter 1, union 3 -> IoU RN(1/3)
+    third = np.float32(1.0) / np.float32(3.0)
+    for boxes, thr in (([a, b], np.float32(0.5)), ([c, d], third)):
+        boxes = np.array(boxes, np.float32)
+        for t in (thr, np.nextafter(thr, np.float32(0)), np.nextafter(thr, np.float32(1))):
+            ref = T.non_max_suppression(boxes[:, [1, 0, 3, 2]], np.array([2, 1], np.float32), 2, float(t))
+            got = ops().nms_sorted(boxes, float(t), 2)
+            np.testing.assert_array_equal(got, ref)
+        assert len(ops().nms_sorted(boxes, float(thr), 2)) == 2                               # equal: both kept
+        assert len(ops().nms_sorted(boxes, float(np.nextafter(thr, np.float32(0))), 2)) == 1  # one ulp lower: suppressed
+
+
+def test_nms_all_duplicates_and_all_degenerate():
+    boxes = np.tile(np.array([[5, 5, 50, 60]], np.float32), (300, 1))
+    np.testing.assert_array_equal(ops().nms_sorted(boxes, 0.7, 300), [0])
+    flat = np.tile(np.array([[5, 5, 5, 60]], np.float32), (130, 1))          # zero area: IoU 0, nothing suppressed
+    ref = T.non_max_suppression(flat[:, [1, 0, 3, 2]], np.arange(130, 0, -1).astype(np.float32), 130, 0.7)
+    np.testing.assert_array_equal(ops().nms_sorted(flat, 0.7, 130), ref)
+
+
 RPN_CFG = {'pre_nms_top_n': 4, 'post_nms_top_n': 3, 'nms_threshold': 1, 'min_size': 0, 'clip_after_nms': False,
            'filter_outside_anchors': False, 'apply_nms': True, 'min_prob_threshold': 0.0}
 
