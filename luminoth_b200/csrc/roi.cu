@@ -70,24 +70,28 @@ __device__ __forceinline__ void row_interp(const float* f, size_t rowbase, int c
   }
 }
 
-template <int CPL>
+// RB consecutive ROIs per CTA: their RB*49 pooled cells are dealt round-robin to the 8 warps.  With one ROI per
+// CTA, 49 cells on 8 warps leave seven warps idle for 1/8 of the CTA's life (ncu: 10 % of all samples stalled at the
+// final barrier); with four ROIs the imbalance is 196 = 8*24 + 4 -> 2 %.
+template <int CPL, int RB>
 __global__ void __launch_bounds__(256, CPL == 8 ? 2 : 3) roi_pool_kernel(const RoiArgs a) {
   constexpr int SLICE = 32 * CPL;             // channels per CTA (one warp-wide vector of CPL channels per lane)
-  const int row = blockIdx.x;                 // global roi row = img*rmax + r
-  const int img = row / a.rmax, r = row % a.rmax;
+  const int row0 = blockIdx.x * RB;           // first global roi row (= img*rmax + r) of this CTA
+  const int rows_total = a.n * a.rmax;
   const int cslice = blockIdx.y * SLICE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = cslice + lane * CPL;
   const int oh = a.crop_h >> 1, ow = a.crop_w >> 1;
-  const bool live = (a.counts == nullptr || r < a.counts[img]) && c0 < a.c;
-  const size_t obase = (size_t)row * oh * ow * a.c;
-  const float* f = a.fmap + (size_t)img * a.fh * a.fw * a.c;
+  const int ncell = oh * ow;
 
-  // sample tables: crop_h y-samples then crop_w x-samples (TF crop_and_resize arithmetic, once per CTA)
-  __shared__ Samp samp[64];
-  if ((int)threadIdx.x < a.crop_h + a.crop_w) {
-    const bool is_y = (int)threadIdx.x < a.crop_h;
-    const int k = is_y ? threadIdx.x : threadIdx.x - a.crop_h;
+  // sample tables: crop_h y-samples then crop_w x-samples (TF crop_and_resize arithmetic, once per CTA and ROI)
+  __shared__ Samp samp_all[RB][64];
+  const int nsamp = a.crop_h + a.crop_w;
+  if ((int)threadIdx.x < RB * nsamp && row0 + (int)threadIdx.x / nsamp < rows_total) {
+    const int rl_ = threadIdx.x / nsamp, ts = threadIdx.x % nsamp;
+    const int row = row0 + rl_;
+    const bool is_y = ts < a.crop_h;
+    const int k = is_y ? ts : ts - a.crop_h;
     const float* rb = a.rois + (size_t)row * 4;
     // normalised box, TF order (y1,x1,y2,x2): divided by the IMAGE size (quirk Q3)
     const float lo_n = is_y ? __fdiv_rn(rb[1], a.im_h) : __fdiv_rn(rb[0], a.im_w);
@@ -102,14 +106,25 @@ __global__ void __launch_bounds__(256, CPL == 8 ? 2 : 3) roi_pool_kernel(const R
     s.lo = s.ok ? (int)floorf(in) : 0;
     s.hi = s.ok ? (int)ceilf(in) : 0;
     s.lerp = __fsub_rn(in, (float)s.lo);
-    samp[threadIdx.x] = s;
+    samp_all[rl_][ts] = s;
   }
   __syncthreads();
 
+  __shared__ float part[RB][8][SLICE];        // per-warp partial sums of the fused spatial mean
   float msum[CPL];
 #pragma unroll
   for (int j = 0; j < CPL; ++j) msum[j] = 0.f;
-  for (int cell = warp; cell < oh * ow; cell += 8) {
+  for (int rl = 0; rl < RB; ++rl) {
+    const int row = row0 + rl;
+    if (row >= rows_total) break;
+    const int img = row / a.rmax, r = row - img * a.rmax;
+    const bool live = (a.counts == nullptr || r < a.counts[img]) && c0 < a.c;
+    const size_t obase = (size_t)row * ncell * a.c;
+    const float* f = a.fmap + (size_t)img * a.fh * a.fw * a.c;
+    const Samp* samp = samp_all[rl];
+    // the RB*ncell cells of the CTA are dealt round-robin: this warp's first cell inside ROI rl
+    const int first = (((warp - rl * ncell) % 8) + 8) % 8;
+  for (int cell = first; cell < ncell; cell += 8) {
     if (c0 >= a.c) break;
     const int py = cell / ow, px = cell % ow;
     float best[CPL];
@@ -182,21 +197,25 @@ __global__ void __launch_bounds__(256, CPL == 8 ? 2 : 3) roi_pool_kernel(const R
       }
     }
   }
-  if (a.mhi) {            // fused spatial mean (rcnn.py:188): warp partials -> fixed-order sum -> / cells
-    __shared__ float part[8][SLICE];
+    if (a.mhi) {          // this warp's share of ROI rl
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) part[warp][lane * CPL + j] = msum[j];
+      for (int j = 0; j < CPL; ++j) { part[rl][warp][lane * CPL + j] = msum[j]; msum[j] = 0.f; }
+    }
+  }
+  if (a.mhi) {            // fused spatial mean (rcnn.py:188): warp partials -> fixed-order sum -> / cells
     __syncthreads();
     const int ch = cslice + threadIdx.x;
     if ((int)threadIdx.x < SLICE && ch < a.c) {
-      float s = 0.f;
+      for (int rl = 0; rl < RB && row0 + rl < rows_total; ++rl) {
+        float s = 0.f;
 #pragma unroll
-      for (int w8 = 0; w8 < 8; ++w8) s += part[w8][threadIdx.x];
-      const float v = __fdiv_rn(s, (float)(oh * ow));
-      __half h, l;
-      split_f32(v, h, l);
-      a.mhi[(size_t)row * a.c + ch] = h;
-      a.mlo[(size_t)row * a.c + ch] = l;
+        for (int w8 = 0; w8 < 8; ++w8) s += part[rl][w8][threadIdx.x];
+        const float v = __fdiv_rn(s, (float)ncell);
+        __half h, l;
+        split_f32(v, h, l);
+        a.mhi[(size_t)(row0 + rl) * a.c + ch] = h;
+        a.mlo[(size_t)(row0 + rl) * a.c + ch] = l;
+      }
     }
   }
 }
@@ -217,12 +236,19 @@ void launch_roi_pool(const float* fmap_f32, int n, int fh, int fw, int c, const 
   static const int cpl = [] { const char* e = getenv("LUMI_ROI_CPL"); return (e && atoi(e) == 4) ? 4 : 8; }();
   // (measured alternatives at R = 2000, batch 8: 4 channels/lane 3.1 ms, straight-line 16-tap loads
   //  without sharing 3.0 ms, this kernel 2.7 ms)
+  static const int rb = [] { const char* e = getenv("LUMI_ROI_RB"); return (e && atoi(e) == 1) ? 1 : 4; }();
+  LUMI_REQUIRE(pw * 2 + ph * 2 <= 64, "roi_pool: pooled size too large");
   if (cpl == 8) {
-    dim3 grid((unsigned)rows, (unsigned)cdiv(c, 256));
-    roi_pool_kernel<8><<<grid, 256, 0, st>>>(a);
+    if (rb == 4 && 4 * (a.crop_h + a.crop_w) <= 256) {
+      dim3 grid((unsigned)cdiv64(rows, 4), (unsigned)cdiv(c, 256));
+      roi_pool_kernel<8, 4><<<grid, 256, 0, st>>>(a);
+    } else {
+      dim3 grid((unsigned)rows, (unsigned)cdiv(c, 256));
+      roi_pool_kernel<8, 1><<<grid, 256, 0, st>>>(a);
+    }
   } else {                 // 4 channels per lane: half the registers (measured slower: 3.1 vs 2.7 ms at R = 2000)
     dim3 grid((unsigned)rows, (unsigned)cdiv(c, 128));
-    roi_pool_kernel<4><<<grid, 256, 0, st>>>(a);
+    roi_pool_kernel<4, 1><<<grid, 256, 0, st>>>(a);
   }
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
