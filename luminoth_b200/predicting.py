@@ -78,6 +78,29 @@ def format_predictions(objects, labels, probs, scale_factor, class_labels=None):
                   key=lambda x: x['prob'], reverse=True)
 
 
+def load_checkpoint_weights(engine, job_dir):
+    """The ``Saver.restore`` of ``predicting.py:51-63`` without TensorFlow: reads the latest Saver-V2 bundle under
+    ``job_dir`` and returns {tf variable name: array} for exactly the variables the engine's plan uses (optimizer
+    slots, ``global_step`` and never-executed layers such as ResNet-50's block4 are ignored, like a Saver built from
+    the inference graph would).  Raises ``ValueError`` when the directory holds no checkpoint, a variable is
+    missing or a shape differs."""
+    from . import tf_checkpoint as tfc
+    prefix = tfc.latest_checkpoint(job_dir)                # ValueError('Could not find checkpoint in ...')
+    reader = tfc.BundleReader(prefix)
+    weights, missing = {}, []
+    for name, shape in engine.weight_specs():
+        if not reader.has_tensor(name):
+            missing.append(name)
+            continue
+        if tuple(reader.shape(name)) != tuple(shape):
+            raise ValueError("checkpoint variable '%s' has shape %s, the model expects %s"
+                             % (name, tuple(reader.shape(name)), tuple(shape)))
+        weights[name] = reader.get_tensor(name).astype(np.float32, copy=False)
+    if missing:
+        raise ValueError('checkpoint %s lacks %d model variables, e.g. %s' % (prefix, len(missing), missing[:3]))
+    return weights
+
+
 class PredictorNetwork(object):
     """Instantiates a network in order to get predictions from it.
 
@@ -103,12 +126,12 @@ class PredictorNetwork(object):
                 job_dir = config.train.job_dir
                 if config.train.run_name:
                     job_dir = os.path.join(job_dir, config.train.run_name)
-                # TF Saver-V2 bundle import is the next row; until
-                # then a configured checkpoint directory is an error, never silently ignored.
-                raise ValueError('Could not find checkpoint in {}.'.format(job_dir))
-            warnings.warn('Could not load checkpoint. Using initialized model.')
-            from .synth import make_weights
-            weights = make_weights(config, seed=config.train.seed or 0, profile='reference')
+                # predicting.py:51-63: latest checkpoint of <job_dir>/<run_name>, restored by variable name
+                weights = load_checkpoint_weights(self.engine, job_dir)
+            else:
+                warnings.warn('Could not load checkpoint. Using initialized model.')
+                from .synth import make_weights
+                weights = make_weights(config, seed=config.train.seed or 0, profile='reference')
         self.engine.load_weights(weights).finalize()
 
     # -- reference API

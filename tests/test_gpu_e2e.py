@@ -312,3 +312,30 @@ def test_engine_capacity_is_not_part_of_the_result():
     with pytest.raises((ValueError, RuntimeError)):
         big.predict_raw(synth.make_images(1, 300, 400, seed=1))        # larger than the planned maximum
     big.close(); tight.close()
+
+
+def test_predictor_network_restores_a_saver_v2_checkpoint(tmp_path):
+    """predicting.py:51-63 without TensorFlow: a job_dir holding `checkpoint` + model.ckpt-N.{index,data-*} (the layout
+    of the reference's published checkpoints) gives exactly the detections of the same weights passed in memory."""
+    from luminoth_b200 import tf_checkpoint as tfc
+    from luminoth_b200.predicting import PredictorNetwork
+    cfg = frcnn_cfg('resnet_v1_50')
+    wts = synth.make_weights(cfg, seed=11)
+    run = tmp_path / 'jobs' / 'my-run'
+    run.mkdir(parents=True)
+    extra = dict(wts)
+    extra['global_step'] = np.array(90000, np.int64)                          # things a training run also saves
+    extra['fasterrcnn/rpn/conv/w/Momentum'] = np.zeros_like(wts['fasterrcnn/rpn/conv/w'])
+    tfc.write_bundle(str(run / 'model.ckpt-90000'), extra)
+    tfc.write_checkpoint_state(str(run), 'model.ckpt-90000')
+    img = synth.make_images(1, 160, 224, seed=12)[0]
+    ref_net = PredictorNetwork(frcnn_cfg('resnet_v1_50'), weights=wts)
+    want = ref_net.predict_image(img)
+    ref_net.engine.close()
+    cfg2 = frcnn_cfg('resnet_v1_50', ['train.job_dir=' + str(tmp_path / 'jobs'), 'train.run_name=my-run'])
+    net = PredictorNetwork(cfg2)
+    got = net.predict_image(img)
+    net.engine.close()
+    assert got == want and len(got) > 0
+    with pytest.raises(ValueError, match='Could not find checkpoint'):
+        PredictorNetwork(frcnn_cfg('resnet_v1_50', ['train.job_dir=' + str(tmp_path / 'empty')]))
