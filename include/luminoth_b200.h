@@ -67,6 +67,12 @@ int lumi_finalize(lumi_engine* e);
 int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n, int h, int w,
                  float* boxes, float* scores, int32_t* labels, int32_t* counts, int outputs_on_device);
 
+/* Same call for float32 images [n,h,w,3]: what the reference's graph sees when the dataset preprocessing
+ * resized the input (utils/image.py:38-147 produces non-integer pixel values; predicting.py:110-112 feeds them
+ * as they are).  lumi_predict is the exact special case of integer-valued pixels. */
+int lumi_predict_f32(lumi_engine* e, const float* images, int images_on_device, int n, int h, int w,
+                     float* boxes, float* scores, int32_t* labels, int32_t* counts, int outputs_on_device);
+
 int lumi_max_detections(lumi_engine* e);
 void* lumi_stream(lumi_engine* e);            /* cudaStream_t the engine launches on */
 int lumi_synchronize(lumi_engine* e);
@@ -127,6 +133,10 @@ const char* lumi_op_last_error(void);      /* message of the last failed lumi_op
 int lumi_op_conv2d(const float* x, int n, int h, int w, int cin, const float* wgt, int kh, int kw, int cout,
                    int stride, int rate, int padding, const float* scale, const float* bias,
                    const float* residual, int act, int impl, float* y, int* ho, int* wo, void* stream);
+
+/* tf.image.resize_images(BILINEAR) of TF 1.x (legacy kernel, align_corners=False) on one HWC image with 3 channels,
+ * utils/image.py:94-97,139-142.  src: DEVICE uint8 (src_is_f32 = 0) or float32 (1) [h0,w0,3]; dst DEVICE float32 [h,w,3]. */
+int lumi_op_resize_bilinear(const void* src, int src_is_f32, int h0, int w0, float* dst, int h, int w, void* stream);
 
 /* max_pool NHWC fp32. padding 0 VALID / 1 SAME. */
 int lumi_op_max_pool(const float* x, int n, int h, int w, int c, int k, int stride, int padding, float* y, void* stream);

@@ -5,7 +5,8 @@ namespace lumi {
 
 // uint8 RGB image -> (optionally mean-subtracted) fp16x2 planes.
 // base_network.py:153-177 (`inputs - [means]`, only for resnet*/vgg* architectures).
-__global__ void u8_to_act_kernel(const uint8_t* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo,
+template <typename PIX>
+__global__ void u8_to_act_kernel(const PIX* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo,
                                  size_t numel, int c, float m0, float m1, float m2) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= numel) return;
@@ -16,11 +17,52 @@ __global__ void u8_to_act_kernel(const uint8_t* __restrict__ img, __half* __rest
   split_f32(v, h, l);
   hi[i] = h; lo[i] = l;
 }
-void launch_u8_to_act(const uint8_t* img, Act out, const float* means, cudaStream_t st) {
+void launch_u8_to_act(const void* img, bool img_f32, Act out, const float* means, cudaStream_t st) {
   size_t n = out.numel();
   if (!n) return;
   float m0 = means ? means[0] : 0.f, m1 = means ? means[1] : 0.f, m2 = means ? means[2] : 0.f;
-  u8_to_act_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(img, out.hi, out.lo, n, out.c, m0, m1, m2);
+  if (img_f32)
+    u8_to_act_kernel<float><<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(static_cast<const float*>(img), out.hi, out.lo, n,
+                                                                      out.c, m0, m1, m2);
+  else
+    u8_to_act_kernel<uint8_t><<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(static_cast<const uint8_t*>(img), out.hi,
+                                                                        out.lo, n, out.c, m0, m1, m2);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+// tf.image.resize_images(BILINEAR) of TF 1.x (legacy kernel: align_corners=False, src = dst * (in / out), no
+// half-pixel offset) -- luminoth/utils/image.py:94-97,139-142.  Same float32 operation order as the oracle
+// (tf_ops.resize_bilinear), no FMA contraction, so the result is bit-identical to it.
+template <typename PIX>
+__global__ void resize_bilinear_kernel(const PIX* __restrict__ src, int h0, int w0, float* __restrict__ dst, int h, int w,
+                                       float hs, float ws) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)h * w) return;
+  const int x = (int)(i % w), y = (int)(i / w);
+  const float fy = __fmul_rn((float)y, hs), fx = __fmul_rn((float)x, ws);
+  const int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+  const int y1 = min(y0 + 1, h0 - 1), x1 = min(x0 + 1, w0 - 1);
+  const float yl = __fsub_rn(fy, (float)y0), xl = __fsub_rn(fx, (float)x0);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float tl = (float)src[((size_t)y0 * w0 + x0) * 3 + c], tr = (float)src[((size_t)y0 * w0 + x1) * 3 + c];
+    const float bl = (float)src[((size_t)y1 * w0 + x0) * 3 + c], br = (float)src[((size_t)y1 * w0 + x1) * 3 + c];
+    const float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), xl));
+    const float bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), xl));
+    dst[i * 3 + c] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), yl));
+  }
+}
+void launch_resize_bilinear(const void* src, bool src_f32, int h0, int w0, float* dst, int h, int w, cudaStream_t st) {
+  if (!h || !w) return;
+  const float hs = (float)h0 / (float)h, ws = (float)w0 / (float)w;      // float32 division, like the oracle
+  const size_t total = (size_t)h * w;
+  if (src_f32)
+    resize_bilinear_kernel<float><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(static_cast<const float*>(src), h0, w0,
+                                                                                dst, h, w, hs, ws);
+  else
+    resize_bilinear_kernel<uint8_t><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(static_cast<const uint8_t*>(src), h0,
+                                                                                  w0, dst, h, w, hs, ws);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
@@ -28,7 +70,8 @@ void launch_u8_to_act(const uint8_t* img, Act out, const float* means, cudaStrea
 // Space-to-depth staging of the 7x7/2 stem (slim conv2d_same: zero pad 3/3 AFTER mean subtraction):
 // X2[n][Y][X][dy*6 + dx*3 + c] = xp[2Y+dy][2X+dx][c], xp = padded (image - mean); channels 12..15 = 0.
 // The stem then is a 4x4/1 VALID conv over X2 that the tcgen05 kernel runs as 4 taps of K = 64.
-__global__ void stem_s2d_kernel(const uint8_t* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo, int n,
+template <typename PIX>
+__global__ void stem_s2d_kernel(const PIX* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo, int n,
                                 int h, int w, int h2, int w2, float m0, float m1, float m2) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)n * h2 * w2;
@@ -45,7 +88,7 @@ __global__ void stem_s2d_kernel(const uint8_t* __restrict__ img, __half* __restr
     for (int dx = 0; dx < 2; ++dx) {
       const int py = 2 * Y + dy - 3, px = 2 * X + dx - 3;
       if (py >= 0 && py < h && px >= 0 && px < w) {
-        const uint8_t* p = img + (((size_t)ni * h + py) * w + px) * 3;
+        const PIX* p = img + (((size_t)ni * h + py) * w + px) * 3;
         const float v0 = __fsub_rn((float)p[0], m0), v1 = __fsub_rn((float)p[1], m1), v2 = __fsub_rn((float)p[2], m2);
         const int o = dy * 6 + dx * 3;
         split_f32(v0, ph[o], pl[o]); split_f32(v1, ph[o + 1], pl[o + 1]); split_f32(v2, ph[o + 2], pl[o + 2]);
@@ -55,11 +98,15 @@ __global__ void stem_s2d_kernel(const uint8_t* __restrict__ img, __half* __restr
   uint4* ol = reinterpret_cast<uint4*>(lo + i * 16);
   oh[0] = vh[0]; oh[1] = vh[1]; ol[0] = vl[0]; ol[1] = vl[1];
 }
-void launch_stem_s2d(const uint8_t* img, int n, int h, int w, Act x2, const float* means, cudaStream_t st) {
+void launch_stem_s2d(const void* img, bool img_f32, int n, int h, int w, Act x2, const float* means, cudaStream_t st) {
   size_t total = (size_t)n * x2.h * x2.w;
   if (!total) return;
-  stem_s2d_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(img, x2.hi, x2.lo, n, h, w, x2.h, x2.w, means[0],
-                                                                means[1], means[2]);
+  if (img_f32)
+    stem_s2d_kernel<float><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(static_cast<const float*>(img), x2.hi, x2.lo, n,
+                                                                         h, w, x2.h, x2.w, means[0], means[1], means[2]);
+  else
+    stem_s2d_kernel<uint8_t><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(static_cast<const uint8_t*>(img), x2.hi, x2.lo,
+                                                                           n, h, w, x2.h, x2.w, means[0], means[1], means[2]);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
@@ -67,30 +114,38 @@ void launch_stem_s2d(const uint8_t* img, int n, int h, int w, Act x2, const floa
 // SSD conv1_1 (3x3, C_in = 3) staging for the tensor-core path: zero-padded image with 16-channel
 // pixels (3 real), so that the 64 contiguous fp16 starting at pixel (y, x) are the filter-row window
 // x-1 .. x+2 of row y-1 (the 4th pixel meets zero weights).  uint8 values are exact in fp16: lo = 0.
-__global__ void pack_c3_kernel(const uint8_t* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo, int n,
+template <typename PIX>
+__global__ void pack_c3_kernel(const PIX* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo, int n,
                                int h, int w, int h2, int w2) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)n * h2 * w2;
   if (i >= total) return;
   const int X = (int)(i % w2), Y = (int)((i / w2) % h2), ni = (int)(i / ((size_t)w2 * h2));
-  uint4 vh[2];
+  uint4 vh[2], vl[2];
   __half* ph = reinterpret_cast<__half*>(vh);
+  __half* pl = reinterpret_cast<__half*>(vl);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) ph[j] = __float2half_rn(0.f);
+  for (int j = 0; j < 16; ++j) { ph[j] = __float2half_rn(0.f); pl[j] = __float2half_rn(0.f); }
   const int py = Y - 1, px = X - 1;
   if (py >= 0 && py < h && px >= 0 && px < w) {
-    const uint8_t* p = img + (((size_t)ni * h + py) * w + px) * 3;
-    ph[0] = __float2half_rn((float)p[0]); ph[1] = __float2half_rn((float)p[1]); ph[2] = __float2half_rn((float)p[2]);
+    const PIX* p = img + (((size_t)ni * h + py) * w + px) * 3;
+    // uint8 pixels are exact in fp16 (lo = 0); resized float pixels keep their low part
+    split_f32((float)p[0], ph[0], pl[0]); split_f32((float)p[1], ph[1], pl[1]); split_f32((float)p[2], ph[2], pl[2]);
   }
   uint4* oh = reinterpret_cast<uint4*>(hi + i * 16);
   uint4* ol = reinterpret_cast<uint4*>(lo + i * 16);
   oh[0] = vh[0]; oh[1] = vh[1];
-  ol[0] = make_uint4(0u, 0u, 0u, 0u); ol[1] = make_uint4(0u, 0u, 0u, 0u);
+  ol[0] = vl[0]; ol[1] = vl[1];
 }
-void launch_pack_c3(const uint8_t* img, int n, int h, int w, Act x2, cudaStream_t st) {
+void launch_pack_c3(const void* img, bool img_f32, int n, int h, int w, Act x2, cudaStream_t st) {
   size_t total = (size_t)n * x2.h * x2.w;
   if (!total) return;
-  pack_c3_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(img, x2.hi, x2.lo, n, h, w, x2.h, x2.w);
+  if (img_f32)
+    pack_c3_kernel<float><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(static_cast<const float*>(img), x2.hi, x2.lo, n, h,
+                                                                        w, x2.h, x2.w);
+  else
+    pack_c3_kernel<uint8_t><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(static_cast<const uint8_t*>(img), x2.hi, x2.lo,
+                                                                          n, h, w, x2.h, x2.w);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }

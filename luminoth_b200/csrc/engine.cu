@@ -539,6 +539,7 @@ struct Ctx {
   float* final_keys = nullptr;  // scratch of the final top-k sort
   ConvWorkspace* sk = nullptr;  // stream-K scratch of this stream
   bool taps = true;             // record debug taps (first half only)
+  bool img_f32 = false;         // input pixels are float32 (resized images) instead of uint8
   Act act(int n, int h, int w, int c) {
     Act a; a.n = n; a.h = h; a.w = w; a.c = c;
     const size_t bytes = a.numel() * sizeof(__half);
@@ -662,7 +663,7 @@ void ensure_frcnn_anchors(lumi_engine* e, int h, int w, cudaStream_t st) {
   e->anchors_fh = fh; e->anchors_fw = fw;
 }
 
-void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
+void forward_frcnn(Ctx& cx, const void* images, int n, int h, int w) {
   lumi_engine* e = cx.e;
   const int io = cx.img_off;                      // this (half-)batch's slice of the engine-level buffers
   int* prop_counts = e->d_prop_counts + io;
@@ -677,14 +678,14 @@ void forward_frcnn(Ctx& cx, const uint8_t* images, int n, int h, int w) {
     // stem on the tensor cores: mean-subtract + zero-pad + space-to-depth staging, then 4 taps of K=64
     const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
     Act x2 = cx.act(n, ho + 3, wo + 3, 16);
-    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_stem_s2d(images, n, h, w, x2, RGB_MEANS, cx.st); }
+    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_stem_s2d(images, cx.img_f32, n, h, w, x2, RGB_MEANS, cx.st); }
     Act view = x2;                      // Toeplitz view: pixel (y, x) -> the 64 contiguous fp16 starting at x2[y][x]
     view.w = wo; view.c = 64;
     const long pitch[3] = {16, (long)(wo + 3) * 16, (long)(ho + 3) * (wo + 3) * 16};
     x = run_conv(cx, root + "/conv1#s2d", view, 0, nullptr, 1, nullptr, pitch, 2.0 * n * ho * wo * 147.0 * 64.0);
   } else {
     x = cx.act(n, h, w, 3);
-    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_u8_to_act(images, x, RGB_MEANS, cx.st); }  // base_network.py:153-177
+    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_u8_to_act(images, cx.img_f32, x, RGB_MEANS, cx.st); }  // base_network.py:153-177
     x = run_conv(cx, root + "/conv1", x, 2, nullptr, 1, nullptr);        // conv2d_same(64, 7, stride 2) + BN + relu
   }
   x = run_pool(cx, x, 3, 2, true);                                       // pool1 3x3/2 SAME
@@ -861,7 +862,7 @@ void compute_ssd_anchors(lumi_engine* e) {
   e->ssd_total_anchors = (int)(out.size() / 4);
 }
 
-void forward_ssd(Ctx& cx, const uint8_t* images, int n, int h, int w) {
+void forward_ssd(Ctx& cx, const void* images, int n, int h, int w) {
   lumi_engine* e = cx.e;
   LUMI_REQUIRE(h == e->fixed_h && w == e->fixed_w, "SSD expects images of the configured fixed size");
   const std::string s = "ssd/ssd_feature_extractor";
@@ -870,14 +871,14 @@ void forward_ssd(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   if (c11_tc) {
     // conv1_1 on the tensor cores: zero-padded 16-channel staging, Toeplitz view, 3 filter rows of K=64
     Act x2 = cx.act(n, h + 2, w + 3, 16);
-    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_pack_c3(images, n, h, w, x2, cx.st); }   // no mean subtraction (quirk Q7)
+    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_pack_c3(images, cx.img_f32, n, h, w, x2, cx.st); }   // no mean subtraction (quirk Q7)
     Act view = x2;
     view.w = w; view.c = 64;
     const long pitch[3] = {16, (long)(w + 3) * 16, (long)(h + 2) * (w + 3) * 16};
     x = run_conv(cx, s + "/vgg_16/conv1/conv1_1#pack", view, 0, nullptr, 1, nullptr, pitch, 2.0 * n * h * w * 27.0 * 64.0);
   } else {
     x = cx.act(n, h, w, 3);
-    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_u8_to_act(images, x, nullptr, cx.st); }  // no mean subtraction (quirk Q7)
+    if (!cx.dry) { ProfScope ps(cx.e, cx.dry, PC_PREP); launch_u8_to_act(images, cx.img_f32, x, nullptr, cx.st); }  // no mean subtraction (quirk Q7)
   }
   Act fmaps[6];
   for (int b = 0; b < 5; ++b) {
@@ -934,7 +935,7 @@ void forward_ssd(Ctx& cx, const uint8_t* images, int n, int h, int w) {
   }
 }
 
-void forward(Ctx& cx, const uint8_t* images, int n, int h, int w) {
+void forward(Ctx& cx, const void* images, int n, int h, int w) {
   cx.arena->off = 0;
   if (cx.taps) cx.e->taps.clear();
   if (cx.e->type == "fasterrcnn") forward_frcnn(cx, images, n, h, w);
@@ -1101,8 +1102,8 @@ int lumi_finalize(lumi_engine* e) {
   LUMI_API_END(e)
 }
 
-int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n, int h, int w, float* boxes,
-                 float* scores, int32_t* labels, int32_t* counts, int outputs_on_device) {
+static int predict_impl(lumi_engine* e, const void* images, int esz, int images_on_device, int n, int h, int w,
+                        float* boxes, float* scores, int* labels, int* counts, int outputs_on_device) {
   if (!e) return LUMI_EINVAL;
   LUMI_API_BEGIN
   if (!e->finalized) throw Error(LUMI_ESTATE, "lumi_predict before lumi_finalize");
@@ -1123,8 +1124,8 @@ int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n
     e->planned_n = plan_key; e->planned_h = h; e->planned_w = w;
   }
   const uint8_t* dimg = static_cast<const uint8_t*>(images);
-  const size_t img_bytes = (size_t)n * h * w * 3;
-  const size_t bytes_a = (size_t)nA * h * w * 3;
+  const size_t img_bytes = (size_t)n * h * w * 3 * esz;
+  const size_t bytes_a = (size_t)nA * h * w * 3 * esz;
   if (!images_on_device) {
     if (img_bytes > e->images_cap) {
       LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
@@ -1138,6 +1139,7 @@ int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n
   g_launch_count = 0;
   if (e->type == "fasterrcnn") ensure_frcnn_anchors(e, h, w, e->stream);
   Ctx cx = make_ctx(e, false, 0);
+  cx.img_f32 = esz == 4;
   g_conv_sm_reserve = piped ? 8 : 0;
   g_conv_streamk = e->conv_streamk;
   if (piped) {
@@ -1145,6 +1147,7 @@ int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n
     LUMI_CUDA_CHECK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
     Ctx cb = make_ctx(e, false, 1);
     cb.img_off = nA;
+    cb.img_f32 = cx.img_f32;
     // each half uploads its own images on its own stream: the second half's H2D overlaps the first half's kernels
     if (!images_on_device) {
       LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_images, images, bytes_a, cudaMemcpyHostToDevice, e->stream));
@@ -1178,6 +1181,16 @@ int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n
   }
   return LUMI_OK;
   LUMI_API_END(e)
+}
+
+int lumi_predict(lumi_engine* e, const void* images, int images_on_device, int n, int h, int w, float* boxes,
+                 float* scores, int* labels, int* counts, int outputs_on_device) {
+  return predict_impl(e, images, 1, images_on_device, n, h, w, boxes, scores, labels, counts, outputs_on_device);
+}
+
+int lumi_predict_f32(lumi_engine* e, const float* images, int images_on_device, int n, int h, int w, float* boxes,
+                     float* scores, int* labels, int* counts, int outputs_on_device) {
+  return predict_impl(e, images, 4, images_on_device, n, h, w, boxes, scores, labels, counts, outputs_on_device);
 }
 
 int lumi_max_detections(lumi_engine* e) { return e ? e->kmax : 0; }

@@ -5,11 +5,12 @@
 namespace lumi {
 
 // ---- format conversion / preprocessing (elementwise.cu)
-void launch_u8_to_act(const uint8_t* img, Act out, const float* means /*3 or nullptr*/, cudaStream_t st);
+void launch_u8_to_act(const void* img, bool img_f32, Act out, const float* means /*3 or nullptr*/, cudaStream_t st);
 void launch_f32_to_act(const float* x, Act out, cudaStream_t st);
 // x2: (n, Ho+3, Wo+3, 16) space-to-depth staging of the 7x7/2 stem input (see elementwise.cu)
-void launch_stem_s2d(const uint8_t* img, int n, int h, int w, Act x2, const float* means, cudaStream_t st);
-void launch_pack_c3(const uint8_t* img, int n, int h, int w, Act x2 /*(n,h+2,w+3,16)*/, cudaStream_t st);
+void launch_stem_s2d(const void* img, bool img_f32, int n, int h, int w, Act x2, const float* means, cudaStream_t st);
+void launch_resize_bilinear(const void* src, bool src_f32, int h0, int w0, float* dst, int h, int w, cudaStream_t st);
+void launch_pack_c3(const void* img, bool img_f32, int n, int h, int w, Act x2 /*(n,h+2,w+3,16)*/, cudaStream_t st);
 void launch_act_to_f32(Act in, float* y, cudaStream_t st);
 void launch_max_pool(Act in, Act out, int k, int stride, int pad_t, int pad_l, cudaStream_t st);
 void launch_l2norm_scale(Act in, Act out, const float* gamma, float eps, cudaStream_t st);

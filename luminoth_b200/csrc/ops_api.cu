@@ -104,6 +104,16 @@ int lumi_op_conv2d(const float* x, int n, int h, int w, int cin, const float* wg
   OP_END
 }
 
+int lumi_op_resize_bilinear(const void* src, int src_is_f32, int h0, int w0, float* dst, int h, int w, void* stream) {
+  OP_BEGIN
+  LUMI_REQUIRE(src && dst && h0 > 0 && w0 > 0 && h > 0 && w > 0, "resize_bilinear: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  launch_resize_bilinear(src, src_is_f32 != 0, h0, w0, dst, h, w, st);
+  LUMI_CUDA_CHECK(cudaStreamSynchronize(st));
+  return LUMI_OK;
+  OP_END
+}
+
 int lumi_op_max_pool(const float* x, int n, int h, int w, int c, int k, int stride, int padding, float* y, void* stream) {
   OP_BEGIN
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -38,6 +38,8 @@ SIGNATURES = {
     'lumi_predict': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_int]),
+    'lumi_predict_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     'lumi_max_detections': (ctypes.c_int, [ctypes.c_void_p]),
     'lumi_stream': (ctypes.c_void_p, [ctypes.c_void_p]),
     'lumi_synchronize': (ctypes.c_int, [ctypes.c_void_p]),
@@ -57,6 +59,8 @@ SIGNATURES = {
     'lumi_op_conv2d': (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] + [ctypes.c_int] * 6 +
                        [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2 + [ctypes.c_void_p, _c_int_p, _c_int_p,
                                                                       ctypes.c_void_p]),
+    'lumi_op_resize_bilinear': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     'lumi_op_max_pool': (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_void_p]),
     'lumi_op_roi_pool': (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p,
                                                                                 ctypes.c_int, ctypes.c_float,
@@ -183,31 +187,35 @@ class Engine(object):
 
     # ---- forward
     def predict_raw(self, images):
-        """images: uint8 array [n,h,w,3] (numpy -> host path, H2D inside the
-        call; CUDA torch tensor -> device path).  Returns numpy
+        """images: [n,h,w,3] uint8 (``lumi_predict``) or float32 (``lumi_predict_f32``: resized images keep their
+        non-integer pixel values, like the reference's feed); numpy array -> host path, H2D inside the call;
+        CUDA torch tensor -> device path.  Returns numpy
         (boxes [n,K,4], scores [n,K], labels [n,K], counts [n])."""
         on_dev = False
         if isinstance(images, np.ndarray):
-            imgs = np.ascontiguousarray(images, dtype=np.uint8)
+            is_f32 = images.dtype != np.uint8
+            imgs = np.ascontiguousarray(images, dtype=np.float32 if is_f32 else np.uint8)
             n, h, w, c = imgs.shape
             ptr = imgs.ctypes.data
         else:                       # torch tensor
             import torch
-            assert images.dtype == torch.uint8 and images.is_contiguous()
+            assert images.dtype in (torch.uint8, torch.float32) and images.is_contiguous()
+            is_f32 = images.dtype == torch.float32
             n, h, w, c = images.shape
             on_dev = images.is_cuda
             ptr = images.data_ptr()
         if c != 3:
-            raise ValueError('images must be [n,h,w,3] RGB uint8')
+            raise ValueError('images must be [n,h,w,3] RGB')
         k = self.max_detections
         boxes = np.empty((n, k, 4), np.float32)
         scores = np.empty((n, k), np.float32)
         labels = np.empty((n, k), np.int32)
         counts = np.empty((n,), np.int32)
+        fn = self._lib.lumi_predict_f32 if is_f32 else self._lib.lumi_predict
         with self._lock:
-            rc = self._lib.lumi_predict(self._h, ctypes.c_void_p(ptr), int(on_dev), n, h, w,
-                                        boxes.ctypes.data_as(ctypes.c_void_p), scores.ctypes.data_as(ctypes.c_void_p),
-                                        labels.ctypes.data_as(ctypes.c_void_p), counts.ctypes.data_as(ctypes.c_void_p), 0)
+            rc = fn(self._h, ctypes.c_void_p(ptr), int(on_dev), n, h, w,
+                    boxes.ctypes.data_as(ctypes.c_void_p), scores.ctypes.data_as(ctypes.c_void_p),
+                    labels.ctypes.data_as(ctypes.c_void_p), counts.ctypes.data_as(ctypes.c_void_p), 0)
             if rc != LUMI_OK:
                 _raise(rc, self._lib.lumi_last_error(self._h))
         return boxes, scores, labels, counts

@@ -42,22 +42,30 @@ def _resize_bilinear_legacy(image, new_h, new_w):
     return (top + (bot - top) * yl).astype(np.float32)
 
 
-def preprocess_image(image, config):
-    """Inference preprocessing; returns (uint8-compatible float image, scale_factor)."""
-    image = np.asarray(image)
-    if image.ndim != 3 or image.shape[2] != 3:
-        raise ValueError('expected an (H, W, 3) RGB image')
+def target_size(shape, config):
+    """(new_h, new_w, scale_factor) of the inference preprocessing for an image of ``shape`` --
+    ``utils/image.py:38-114`` (aspect-preserving, float32 arithmetic, ``tf.to_int32`` truncation) and
+    ``:117-147`` (fixed size; scale_factor is then the tuple (s_h, s_w))."""
     ip = config['dataset']['image_preprocessing']
     f32 = np.float32
-    h, w = f32(image.shape[0]), f32(image.shape[1])
+    h, w = f32(shape[0]), f32(shape[1])
     if ip.get('fixed_height') and ip.get('fixed_width'):
         nh, nw = int(ip['fixed_height']), int(ip['fixed_width'])
-        return _resize_bilinear_legacy(image, nh, nw), (f32(nh) / h, f32(nw) / w)
+        return nh, nw, (f32(nh) / h, f32(nw) / w)
     mn, mx = ip.get('min_size'), ip.get('max_size')
     up = max(f32(mn) / min(h, w), f32(1.)) if mn is not None else f32(1.)
     down = min(f32(mx) / max(h, w), f32(1.)) if mx is not None else f32(1.)
     scale = f32(up * down)
-    nh, nw = int(math.trunc(float(h * scale))), int(math.trunc(float(w * scale)))
+    return int(math.trunc(float(h * scale))), int(math.trunc(float(w * scale))), scale
+
+
+def preprocess_image(image, config):
+    """Inference preprocessing on the host (numpy); returns (float32 image, scale_factor).  The product path
+    resizes on the GPU (``PredictorNetwork._resize_on_device``); this restatement is its cross-check."""
+    image = np.asarray(image)
+    if image.ndim != 3 or image.shape[2] != 3:
+        raise ValueError('expected an (H, W, 3) RGB image')
+    nh, nw, scale = target_size(image.shape, config)
     return _resize_bilinear_legacy(image, nh, nw), scale
 
 
@@ -140,19 +148,44 @@ class PredictorNetwork(object):
 
     # -- batched extension
     def predict_batch(self, images):
-        pre = [preprocess_image(np.asarray(im), self.config) for im in images]
-        shapes = {p[0].shape for p in pre}
-        if len(shapes) != 1:
-            raise ValueError('predict_batch needs images that preprocess to one size; got %s' % sorted(shapes))
-        # the reference feeds the resized float image; the engine ingests uint8 pixels
-        # (exact for unresized uint8 inputs -- the identity path at the benchmark shapes)
-        batch = np.stack([np.clip(np.rint(p[0]), 0, 255).astype(np.uint8) for p in pre])
+        images = [np.asarray(im) for im in images]
+        for im in images:
+            if im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError('expected an (H, W, 3) RGB image')
+        sizes = [target_size(im.shape, self.config) for im in images]
+        if len({(nh, nw) for nh, nw, _ in sizes}) != 1:
+            raise ValueError('predict_batch needs images that preprocess to one size; got %s'
+                             % sorted({(nh, nw) for nh, nw, _ in sizes}))
+        nh, nw = sizes[0][0], sizes[0][1]
+        untouched = all(im.dtype == np.uint8 and im.shape[:2] == (nh, nw) for im in images)
         out = []
-        for s in range(0, len(batch), self.engine.max_batch):
-            chunk = batch[s:s + self.engine.max_batch]
-            boxes, scores, labels, counts = self.engine.predict_raw(chunk)
+        for s in range(0, len(images), self.engine.max_batch):
+            chunk = images[s:s + self.engine.max_batch]
+            if untouched:       # integer pixels, no resize: the uint8 entry point (the benchmark shapes)
+                batch = np.stack(chunk)
+            else:               # the reference feeds the resized FLOAT image (predicting.py:110-112)
+                batch = self._resize_on_device(chunk, nh, nw)
+            boxes, scores, labels, counts = self.engine.predict_raw(batch)
             for i in range(len(chunk)):
                 k = int(counts[i])
-                out.append(format_predictions(boxes[i, :k], labels[i, :k], scores[i, :k], pre[s + i][1],
+                out.append(format_predictions(boxes[i, :k], labels[i, :k], scores[i, :k], sizes[s + i][2],
                                               self.class_labels))
         return out
+
+    def _resize_on_device(self, images, nh, nw):
+        """``resize_image`` / ``resize_image_fixed`` (utils/image.py:38-147) on the GPU: legacy TF bilinear kernel,
+        bit-identical to the float32 host restatement; returns a CUDA float32 tensor [n, nh, nw, 3]."""
+        import ctypes
+        import torch
+        lib = self.engine._lib
+        dev = torch.device('cuda', self.engine.device)
+        batch = torch.empty((len(images), nh, nw, 3), dtype=torch.float32, device=dev)
+        for i, im in enumerate(images):
+            is_f32 = im.dtype != np.uint8
+            src = torch.from_numpy(np.ascontiguousarray(im, dtype=np.float32 if is_f32 else np.uint8)).to(dev)
+            rc = lib.lumi_op_resize_bilinear(ctypes.c_void_p(src.data_ptr()), int(is_f32), im.shape[0], im.shape[1],
+                                             ctypes.c_void_p(batch[i].data_ptr()), nh, nw, None)
+            if rc != 0:
+                raise RuntimeError(lib.lumi_op_last_error().decode())
+        torch.cuda.synchronize(dev)
+        return batch

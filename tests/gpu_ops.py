@@ -122,3 +122,12 @@ def class_detections(boxes_in, deltas, cls_prob, im_shape, nc, cfg, variances, s
                                         _p(cnt), None))
     k = int(cnt.cpu()[0])
     return obj.cpu().numpy()[:k], lab.cpu().numpy()[:k], prob.cpu().numpy()[:k]
+
+
+def resize_bilinear(image, nh, nw):
+    lib = _lib()
+    is_f32 = image.dtype != np.uint8
+    src = _dev(image, np.float32 if is_f32 else np.uint8)
+    dst = torch.empty((nh, nw, 3), dtype=torch.float32, device='cuda')
+    _check(lib.lumi_op_resize_bilinear(_p(src), int(is_f32), image.shape[0], image.shape[1], _p(dst), nh, nw, None))
+    return dst.cpu().numpy()

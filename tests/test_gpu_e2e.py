@@ -339,3 +339,31 @@ def test_predictor_network_restores_a_saver_v2_checkpoint(tmp_path):
     assert got == want and len(got) > 0
     with pytest.raises(ValueError, match='Could not find checkpoint'):
         PredictorNetwork(frcnn_cfg('resnet_v1_50', ['train.job_dir=' + str(tmp_path / 'empty')]))
+
+
+@pytest.mark.parametrize('shape', [(375, 500), (1200, 1600)])
+def test_predictor_network_resized_images_match_the_reference_feed(shape):
+    """Images that the dataset preprocessing resizes (utils/image.py:38-114: 375x500 -> 600x800 upscaled,
+    1200x1600 -> 768x1024 downscaled) reach the network as FLOAT pixels in the reference (predicting.py:110-112).
+    The product path resizes on the GPU and feeds float32; detections must match the oracle's predict_image on the
+    original image (integer boxes in original-image pixels, probabilities to 1e-4)."""
+    cfg = frcnn_cfg('resnet_v1_50')
+    wts = synth.make_weights(cfg, seed=7)
+    img = synth.make_images(1, shape[0], shape[1], seed=21)[0]
+    net = PredictorNetwork(cfg, weights=wts)
+    got = net.predict_image(img)
+    ref = opredict.predict_image(img, wts, cfg)
+    assert len(got) == len(ref) and len(got) > 0
+    # int(round(coord / scale)) can flip by one pixel when fp32 noise (1e-3 px) meets a .5 boundary: match every
+    # detection to an unused reference row of the same label within 1 px and 1e-4 in probability
+    free = list(ref)
+    exact = 0
+    for g in got:
+        hit = [r for r in free if r['label'] == g['label'] and abs(r['prob'] - g['prob']) <= 1.01e-4
+               and max(abs(a - b) for a, b in zip(g['bbox'], r['bbox'])) <= 1]
+        assert hit, 'no reference detection for %r' % (g,)
+        best = min(hit, key=lambda r: sum(abs(a - b) for a, b in zip(g['bbox'], r['bbox'])))
+        exact += best['bbox'] == g['bbox']
+        free.remove(best)
+    assert exact >= 0.97 * len(got)
+    net.engine.close()

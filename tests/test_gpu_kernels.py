@@ -102,6 +102,21 @@ def test_conv_tc_equals_simt_on_large_k():
     assert_close(c, ref, 2e-5, 'tc')
 
 
+@pytest.mark.parametrize('h0,w0,nh,nw,dtype', [(375, 500, 600, 800, np.uint8), (1200, 1600, 768, 1024, np.uint8),
+                                               (333, 517, 300, 300, np.uint8), (64, 48, 64, 48, np.uint8),
+                                               (97, 131, 600, 810, np.float32)])
+def test_resize_bilinear_bit_exact(h0, w0, nh, nw, dtype):
+    """utils/image.py:94-97,139-142 (tf.image.resize_images BILINEAR, TF1 legacy kernel): the GPU kernel follows the
+    oracle's float32 operation order without FMA contraction -- identical bits."""
+    rng = np.random.default_rng(h0 + nw)
+    img = rng.integers(0, 256, (h0, w0, 3)).astype(dtype)
+    if dtype == np.float32:
+        img = img + rng.uniform(0, 1, img.shape).astype(np.float32)
+    ref = T.resize_bilinear(img.astype(np.float32), nh, nw)
+    got = ops().resize_bilinear(img, nh, nw)
+    np.testing.assert_array_equal(got, ref)
+
+
 @pytest.mark.parametrize('k,stride,padding,h,w', [(3, 2, 'SAME', 300, 512), (2, 2, 'VALID', 75, 75),
                                                     (3, 1, 'SAME', 18, 18), (2, 2, 'VALID', 14, 14)])
 def test_max_pool(k, stride, padding, h, w):
