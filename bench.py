@@ -107,6 +107,30 @@ def build_config(wl):
     return default_config(wl['model'], wl['overrides'])
 
 
+def best_thread_count(cfg, wts, wl):
+    """The oracle's convolutions run on torch's CPU thread pool; more threads is not always faster (128 threads on
+    the GPU box measured 2x SLOWER than torchrun's OMP_NUM_THREADS=1 default).  Give the CPU arm its best setting:
+    time one small forward per candidate and keep the fastest."""
+    import torch
+    from luminoth_b200 import synth
+    from oracle import predict as opredict
+    ncpu = os.cpu_count() or 1
+    cands = sorted({max(1, c) for c in (ncpu, ncpu // 2, ncpu // 4, 32, 16, 8, 1) if c <= ncpu}, reverse=True)
+    h, w = (wl['h'], wl['w']) if wl['model'] == 'ssd' else (wl['h'] // 2, wl['w'] // 2)
+    img = synth.make_images(1, h, w, seed=7)[0]
+    best, best_t = cands[0], None
+    for c in cands:
+        torch.set_num_threads(c)
+        opredict.network_outputs(img, wts, cfg)
+        t0 = time.perf_counter()
+        opredict.network_outputs(img, wts, cfg)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_oracle_images_per_s(cfg, wts, wl, n_images, threads):
     """The CPU restatement of the reference forward (oracle/), timed one image at a time."""
     import torch
@@ -131,8 +155,7 @@ def run_reference(args, wl):
     from oracle import predict as opredict
     cfg = build_config(wl)
     wts = synth.make_weights(cfg, seed=0, profile='peaky')
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
+    threads = best_thread_count(cfg, wts, wl)
     imgs = synth.make_images(max(1, min(args.steps + args.warmup, 4)), wl['h'], wl['w'], seed=123)
     budget_s = 240.0
     t_start = time.perf_counter()
@@ -154,7 +177,9 @@ def run_reference(args, wl):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': wl['name'], 'sample': '1 image of the batch per step'},
             'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
-                             'sample': '%d images, one per step (oracle port of the reference forward; TF1 not installable)' % done},
+                             'sample': '%d images, one per step (oracle port of the reference forward; TF1 not '
+                                       'installable); thread count picked as the fastest of a calibration sweep up to '
+                                       '%d host threads' % (done, os.cpu_count() or 1)},
             'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
@@ -170,6 +195,8 @@ def run_ours(args, wl):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -342,14 +369,15 @@ def run_ours(args, wl):
                                    'tflops': (w_ / c) / (ms_ / c * 1e-3) / 1e12 if ms_ > 0 else None}
                                   for n, c, ms_, w_ in layer_prof]
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
             if wts is None:
                 wts = synth.make_weights(cfg, seed=0, profile='peaky')
+            threads = best_thread_count(cfg, wts, wl)
             n_cpu = 2 if wl['model'] == 'fasterrcnn' else 8
             cv, cdt = cpu_oracle_images_per_s(cfg, wts, wl, n_cpu, threads)
             out['cpu_baseline'] = {'value': cv, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
-                                   'sample': '%d images of the same workload, one at a time, %.1f s '
-                                             '(oracle port of the reference forward; TF1 not installable)' % (n_cpu, cdt)}
+                                   'sample': '%d images of the same workload, one at a time, %.1f s (oracle port of the '
+                                             'reference forward; TF1 not installable; thread count = fastest of a sweep up '
+                                             'to %d host threads)' % (n_cpu, cdt, os.cpu_count() or 1)}
         print(json.dumps(out), flush=True)
     # teardown order matters: tensors that lived on the engine's (external) stream must be released, and the
     # process group torn down, BEFORE the engine destroys that stream
