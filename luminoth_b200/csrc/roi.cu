@@ -73,8 +73,8 @@ __device__ __forceinline__ void row_interp(const float* f, size_t rowbase, int c
 // RB consecutive ROIs per CTA: their RB*49 pooled cells are dealt round-robin to the 8 warps.  With one ROI per
 // CTA, 49 cells on 8 warps leave seven warps idle for 1/8 of the CTA's life (ncu: 10 % of all samples stalled at the
 // final barrier); with four ROIs the imbalance is 196 = 8*24 + 4 -> 2 %.
-template <int CPL, int RB>
-__global__ void __launch_bounds__(256, CPL == 8 ? 2 : 3) roi_pool_kernel(const RoiArgs a) {
+template <int CPL, int RB, int NW>
+__global__ void __launch_bounds__(32 * NW, (CPL == 8 ? 2 : 3) * (8 / NW)) roi_pool_kernel(const RoiArgs a) {
   constexpr int SLICE = 32 * CPL;             // channels per CTA (one warp-wide vector of CPL channels per lane)
   const int row0 = blockIdx.x * RB;           // first global roi row (= img*rmax + r) of this CTA
   const int rows_total = a.n * a.rmax;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256, CPL == 8 ? 2 : 3) roi_pool_kernel(const R
   }
   __syncthreads();
 
-  __shared__ float part[RB][8][SLICE];        // per-warp partial sums of the fused spatial mean
+  __shared__ float part[RB][NW][SLICE];       // per-warp partial sums of the fused spatial mean
   float msum[CPL];
 #pragma unroll
   for (int j = 0; j < CPL; ++j) msum[j] = 0.f;
@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(256, CPL == 8 ? 2 : 3) roi_pool_kernel(const R
     const float* f = a.fmap + (size_t)img * a.fh * a.fw * a.c;
     const Samp* samp = samp_all[rl];
     // the RB*ncell cells of the CTA are dealt round-robin: this warp's first cell inside ROI rl
-    const int first = (((warp - rl * ncell) % 8) + 8) % 8;
-  for (int cell = first; cell < ncell; cell += 8) {
+    const int first = (((warp - rl * ncell) % NW) + NW) % NW;
+  for (int cell = first; cell < ncell; cell += NW) {
     if (c0 >= a.c) break;
     const int py = cell / ow, px = cell % ow;
     float best[CPL];
@@ -143,11 +143,13 @@ __global__ void __launch_bounds__(256, CPL == 8 ? 2 : 3) roi_pool_kernel(const R
       }
 #pragma unroll
       for (int sx = 0; sx < 2; ++sx) {
-        const bool ok = y0.ok && (sx ? x1.ok : x0.ok);
+        const bool ok = y0.ok && (sx ? x1.ok : x0.ok);          // warp-uniform
+        if (ok) {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          const float v = ok ? fmaf(b0[sx][j] - t0[sx][j], y0.lerp, t0[sx][j]) : 0.f;
-          best[j] = fmaxf(best[j], v);              // extrapolation_value = 0
+          for (int j = 0; j < CPL; ++j) best[j] = fmaxf(best[j], fmaf(b0[sx][j] - t0[sx][j], y0.lerp, t0[sx][j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) best[j] = fmaxf(best[j], 0.f);              // extrapolation_value = 0
         }
       }
       float t1[2][CPL], b1[2][CPL];
@@ -172,10 +174,12 @@ __global__ void __launch_bounds__(256, CPL == 8 ? 2 : 3) roi_pool_kernel(const R
 #pragma unroll
       for (int sx = 0; sx < 2; ++sx) {
         const bool ok = y1.ok && (sx ? x1.ok : x0.ok);
+        if (ok) {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          const float v = ok ? fmaf(b1[sx][j] - t1[sx][j], y1.lerp, t1[sx][j]) : 0.f;
-          best[j] = fmaxf(best[j], v);
+          for (int j = 0; j < CPL; ++j) best[j] = fmaxf(best[j], fmaf(b1[sx][j] - t1[sx][j], y1.lerp, t1[sx][j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) best[j] = fmaxf(best[j], 0.f);
         }
       }
     }
@@ -204,12 +208,13 @@ __global__ void __launch_bounds__(256, CPL == 8 ? 2 : 3) roi_pool_kernel(const R
   }
   if (a.mhi) {            // fused spatial mean (rcnn.py:188): warp partials -> fixed-order sum -> / cells
     __syncthreads();
-    const int ch = cslice + threadIdx.x;
-    if ((int)threadIdx.x < SLICE && ch < a.c) {
+    for (int i = threadIdx.x; i < SLICE; i += 32 * NW) {
+      const int ch = cslice + i;
+      if (ch >= a.c) break;
       for (int rl = 0; rl < RB && row0 + rl < rows_total; ++rl) {
         float s = 0.f;
 #pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) s += part[rl][w8][threadIdx.x];
+        for (int w8 = 0; w8 < NW; ++w8) s += part[rl][w8][i];
         const float v = __fdiv_rn(s, (float)ncell);
         __half h, l;
         split_f32(v, h, l);
@@ -238,17 +243,23 @@ void launch_roi_pool(const float* fmap_f32, int n, int fh, int fw, int c, const 
   //  without sharing 3.0 ms, this kernel 2.7 ms)
   static const int rb = [] { const char* e = getenv("LUMI_ROI_RB"); return (e && atoi(e) == 1) ? 1 : 4; }();
   LUMI_REQUIRE(pw * 2 + ph * 2 <= 64, "roi_pool: pooled size too large");
+  // 4 warps x 4 ROIs: 196 cells = 49 per warp, no tail at all (measured 2.49 vs 2.51 ms with 8 warps, 2.73 ms with
+  // one ROI per CTA)
+  static const int nw = [] { const char* e = getenv("LUMI_ROI_NW"); return (e && atoi(e) == 8) ? 8 : 4; }();
   if (cpl == 8) {
-    if (rb == 4 && 4 * (a.crop_h + a.crop_w) <= 256) {
+    if (rb == 4 && nw == 4 && 4 * (a.crop_h + a.crop_w) <= 128) {
       dim3 grid((unsigned)cdiv64(rows, 4), (unsigned)cdiv(c, 256));
-      roi_pool_kernel<8, 4><<<grid, 256, 0, st>>>(a);
+      roi_pool_kernel<8, 4, 4><<<grid, 128, 0, st>>>(a);
+    } else if (rb == 4 && 4 * (a.crop_h + a.crop_w) <= 256) {
+      dim3 grid((unsigned)cdiv64(rows, 4), (unsigned)cdiv(c, 256));
+      roi_pool_kernel<8, 4, 8><<<grid, 256, 0, st>>>(a);
     } else {
       dim3 grid((unsigned)rows, (unsigned)cdiv(c, 256));
-      roi_pool_kernel<8, 1><<<grid, 256, 0, st>>>(a);
+      roi_pool_kernel<8, 1, 8><<<grid, 256, 0, st>>>(a);
     }
   } else {                 // 4 channels per lane: half the registers (measured slower: 3.1 vs 2.7 ms at R = 2000)
     dim3 grid((unsigned)rows, (unsigned)cdiv(c, 128));
-    roi_pool_kernel<4, 1><<<grid, 256, 0, st>>>(a);
+    roi_pool_kernel<4, 1, 8><<<grid, 256, 0, st>>>(a);
   }
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
