@@ -40,6 +40,11 @@ WORKLOADS = {
                        name='Faster R-CNN ResNet-101, 300 proposals/img, 80 classes (NMS stress), batch 8 x 600x1024x3'),
     'ssd': dict(model='ssd', batch=32, h=300, w=300, overrides=[],
                 name='SSD VGG-16 300x300 (VOC config, 20 classes), batch 32 synthetic uint8'),
+    # contract self-test only (tests/test_bench_contract.py): seconds on a CPU, not a benchmark
+    'tiny': dict(model='fasterrcnn', batch=2, h=96, w=128,
+                 overrides=['model.base_network.architecture=resnet_v1_50', 'model.network.num_classes=5',
+                            'model.rpn.proposals.post_nms_top_n=50'],
+                 name='contract self-test: Faster R-CNN ResNet-50, 5 classes, batch 2 x 96x128'),
 }
 
 
