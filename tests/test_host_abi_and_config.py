@@ -122,3 +122,24 @@ def test_format_predictions_matches_oracle_finalize():
         a, sa = preprocess_image(img, cfg); b, sb = preprocess(img, cfg)
         np.testing.assert_array_equal(a, b)
         assert np.all(np.asarray(sa) == np.asarray(sb))
+
+
+def test_target_size_matches_oracle_preprocess_shapes():
+    """utils/image.py:38-114 / :117-147: the product wrapper's float32 size arithmetic (used to drive the GPU
+    resize) agrees with the oracle's preprocess on the resulting shape and scale factor."""
+    from luminoth_b200 import default_config
+    from luminoth_b200.predicting import target_size, preprocess_image
+    from oracle import predict as opredict
+    rng = np.random.default_rng(0)
+    for cfg in (default_config('fasterrcnn'), default_config('ssd')):
+        for _ in range(40):
+            h, w = int(rng.integers(40, 2200)), int(rng.integers(40, 2200))
+            img = np.zeros((h, w, 3), np.uint8)
+            ref_img, ref_scale = opredict.preprocess(img, cfg)
+            nh, nw, scale = target_size(img.shape, cfg)
+            assert (nh, nw) == ref_img.shape[:2]
+            assert np.all(np.asarray(scale, np.float32) == np.asarray(ref_scale, np.float32))
+    img = rng.integers(0, 256, (333, 517, 3)).astype(np.uint8)
+    got, _ = preprocess_image(img, default_config('fasterrcnn'))
+    ref, _ = opredict.preprocess(img, default_config('fasterrcnn'))
+    np.testing.assert_array_equal(got, ref)
