@@ -202,3 +202,33 @@ def get_config(config_files, override_params=None):
 def default_config(model_type, override_params=None):
     """Convenience (not in the reference): base config of a model type + overrides."""
     return get_model_config(get_base_config(model_type), None, override_params)
+
+
+def set_prediction_filters(config, min_prob=None, max_detections=None):
+    """The config mutations every caller of ``PredictorNetwork`` applies BEFORE building it:
+
+    * ``lumi predict`` (``predict.py:246-259``): ``max_detections`` (CLI default 100) overwrites
+      ``rcnn.proposals.total_max_detections`` -- or ``rpn.proposals.post_nms_top_n`` when ``with_rcnn`` is off --
+      and ``min_prob`` (CLI default 0.5) overwrites ``min_prob_threshold``;
+    * ``Detector`` (``tasks.py:64-67``) forces ``min_prob_threshold = 0.0`` and filters in Python;
+    * the web server (``tools/server/web.py:97-100``) uses 0.01.
+
+    ``None`` leaves the respective value untouched.  Unknown model types raise ``ValueError`` like the reference."""
+    mtype = config.model.type
+    if mtype == 'fasterrcnn':
+        if max_detections is not None:
+            if config.model.network.get('with_rcnn', False):
+                config.model.rcnn.proposals.total_max_detections = max_detections
+            else:
+                config.model.rpn.proposals.post_nms_top_n = max_detections
+        if min_prob is not None:
+            config.model.rcnn.proposals.min_prob_threshold = min_prob
+    elif mtype == 'ssd':
+        if max_detections is not None:
+            config.model.proposals.total_max_detections = max_detections
+        if min_prob is not None:
+            config.model.proposals.min_prob_threshold = min_prob
+    else:
+        raise ValueError("Model type '{}' not supported".format(mtype))
+    return config
+

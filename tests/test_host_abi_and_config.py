@@ -143,3 +143,19 @@ def test_target_size_matches_oracle_preprocess_shapes():
     got, _ = preprocess_image(img, default_config('fasterrcnn'))
     ref, _ = opredict.preprocess(img, default_config('fasterrcnn'))
     np.testing.assert_array_equal(got, ref)
+
+
+def test_prediction_filters_follow_the_reference_callers():
+    """predict.py:246-259 / tasks.py:64-67 / web.py:97-100 (quirk Q10): where min_prob and max_detections land."""
+    from luminoth_b200 import default_config, set_prediction_filters
+    c = set_prediction_filters(default_config('fasterrcnn'), min_prob=0.5, max_detections=100)
+    assert c.model.rcnn.proposals.total_max_detections == 100 and c.model.rcnn.proposals.min_prob_threshold == 0.5
+    assert c.model.rpn.proposals.post_nms_top_n == 2000
+    c = set_prediction_filters(default_config('fasterrcnn', ['model.network.with_rcnn=False']), 0.5, 100)
+    assert c.model.rpn.proposals.post_nms_top_n == 100 and c.model.rcnn.proposals.total_max_detections == 300
+    c = set_prediction_filters(default_config('ssd'), min_prob=0.01)
+    assert c.model.proposals.min_prob_threshold == 0.01 and c.model.proposals.total_max_detections == 100
+    c = default_config('ssd')
+    c.model.type = 'yolo'
+    with pytest.raises(ValueError, match='not supported'):
+        set_prediction_filters(c, 0.5, 10)
