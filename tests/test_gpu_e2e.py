@@ -367,3 +367,37 @@ def test_predictor_network_resized_images_match_the_reference_feed(shape):
         free.remove(best)
     assert exact >= 0.97 * len(got)
     net.engine.close()
+
+
+def test_full_size_batch_properties():
+    """BASELINE.json's shape (batch 8 x 600x1024, 2000 proposals, 80 classes) is too slow for the CPU oracle, so
+    the full-size run is held to size-independent properties: bit-reproducibility, batch-permutation equivariance
+    and pipelining neutrality (whole-tile conv schedule), sorted scores, rows inside the image, labels in range."""
+    cfg = default_config('fasterrcnn', ['model.base_network.architecture=resnet_v1_50', 'model.network.num_classes=80'])
+    wts = synth.make_weights(cfg, seed=0, profile='peaky')
+    imgs = synth.make_images(8, 600, 1024, seed=33)
+    eng = Engine(cfg, max_batch=8, max_h=600, max_w=1024)
+    eng.load_weights(wts).finalize()
+    a = eng.predict_raw(imgs)
+    b = eng.predict_raw(imgs)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)                      # default schedule: run-to-run identical
+    boxes, scores, labels, counts = a
+    assert counts.min() >= 0 and counts.max() <= eng.max_detections and counts.sum() > 0
+    for i in range(8):
+        k = int(counts[i])
+        assert (np.diff(scores[i, :k]) <= 0).all()
+        assert labels[i, :k].min(initial=0) >= 0 and labels[i, :k].max(initial=0) < 80
+        bx = boxes[i, :k]
+        assert (bx[:, 0] >= 0).all() and (bx[:, 1] >= 0).all() and (bx[:, 2] <= 1023).all() and (bx[:, 3] <= 599).all()
+        assert (bx[:, 2] >= bx[:, 0]).all() and (bx[:, 3] >= bx[:, 1]).all()
+    eng.set_conv_streamk('off')
+    base = eng.predict_raw(imgs)
+    perm = np.array([5, 2, 7, 0, 3, 6, 1, 4])
+    shuf = eng.predict_raw(imgs[perm])
+    for x, y in zip(base, shuf):
+        np.testing.assert_array_equal(x[perm], y)                # images are independent units
+    eng.set_pipeline(False)
+    for x, y in zip(base, eng.predict_raw(imgs)):
+        np.testing.assert_array_equal(x, y)                      # two-stream pipeline is bit-neutral
+    eng.close()
