@@ -96,15 +96,22 @@ class ClockSampler(threading.Thread):
 
 
 def conv_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the conv_tc launches of one step, from the committed
-    ncu --set full capture of `bench.py --ncu-range` (profiles/r1_ncu_step_summary.json); None if not captured."""
-    f = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_step_summary.json')
-    try:
-        d = json.load(open(f))[workload]['conv_tc_kernel']
-        return d['dram_bytes'], ('sum of dram__bytes_read+write over the %d conv_tc launches of one step '
-                                 '(profiles/r1_ncu_step_summary.json)' % d['launches'])
-    except Exception:
-        return None, 'not captured'
+    """dram__bytes_read.sum + dram__bytes_write.sum of the conv_tc launches of one step.  ncu cannot run inside a
+    timed bench, so the figure comes from the committed `ncu --set full` capture of `bench.py --ncu-range`
+    (scripts/gpu_evidence.sh -> scripts/ncu_step_summary.py) and is stamped with the commit and date of that capture,
+    so a stale profile is visible as stale; None if this workload was never captured."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name in ('r2_ncu_step_summary.json', 'r1_ncu_step_summary.json'):
+        try:
+            j = json.load(open(os.path.join(here, 'profiles', name)))
+            d = j[workload]['conv_tc_kernel']
+            stamp = j.get('_capture', {})
+            return d['dram_bytes'], ('sum of dram__bytes_read+write over the %d conv_tc launches of one step '
+                                     '(profiles/%s, captured at commit %s on %s)'
+                                     % (d['launches'], name, stamp.get('commit', 'round-1 final'), stamp.get('date', '2026-09-22')))
+        except Exception:
+            continue
+    return None, 'not captured'
 
 
 def build_config(wl):
@@ -243,11 +250,15 @@ def run_ours(args, wl):
     import ctypes
     lib = eng._lib
 
+    if world > 1:
+        # the detection kernel itself writes the packed {count, boxes, scores, labels} row of every image into `rec`
+        # (lumi_set_record_output): the only multi-GPU work on the step path is ONE ncclAllGather
+        eng.set_record_output(rec)
+
     def step_device(i):
         eng.predict_device(imgs_dev[i % NROT], boxes, scores, labels, counts)
         if world > 1:           # detections all-gather (fixed-size padded record per image), on the engine's stream
             with torch.cuda.stream(stream):
-                P.pack_detections(boxes, scores, labels, counts, out=rec)
                 P.all_gather_detections(rec, out=gathered)
 
     def step_host(i):
@@ -257,10 +268,8 @@ def run_ours(args, wl):
                               ctypes.c_void_p(hc.data_ptr()), 0)
         if rc != 0:
             raise RuntimeError(lib.lumi_last_error(eng._h).decode())
-        if world > 1:
+        if world > 1:           # `rec` was written on the device by the same call
             with torch.cuda.stream(stream):
-                P.pack_detections(hb.to(dev, non_blocking=True), hs.to(dev, non_blocking=True),
-                                  hl.to(dev, non_blocking=True), hc.to(dev, non_blocking=True), out=rec)
                 P.all_gather_detections(rec, out=gathered)
             stream.synchronize()
 
@@ -419,11 +428,8 @@ def main():
         from luminoth_b200.engine import load_library
         load_library()          # fail loudly if the CUDA library is missing
         run_ours(args, wl)
-        # The engine library carries its own (static) CUDA runtime next to torch's; skip the interpreter's
-        # static-destructor phase, where the two runtimes tear the primary context down in an undefined order.
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        # normal interpreter exit: the library shares torch's CUDA runtime (-cudart shared, luminoth_b200/build.py),
+        # every engine / tensor / process group was released above, so atexit hooks (and the driver's) run
 
 
 if __name__ == '__main__':

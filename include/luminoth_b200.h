@@ -74,6 +74,14 @@ int lumi_predict_f32(lumi_engine* e, const float* images, int images_on_device, 
                      float* boxes, float* scores, int32_t* labels, int32_t* counts, int outputs_on_device);
 
 int lumi_max_detections(lumi_engine* e);
+
+/* Multi-GPU detection exchange (the reference has no counterpart -- it predicts one image at a time,
+ * tasks.py:146-154): when `device_records` is non-NULL every following lumi_predict ALSO writes, from the same
+ * kernel that writes boxes/scores/labels, one packed float32 row per image
+ *   {count, boxes[kmax][4], scores[kmax], labels[kmax]}      (1 + 6*kmax floats)
+ * into the caller's DEVICE buffer [max_batch][1 + 6*kmax] -- the send buffer of the per-step ncclAllGather.
+ * NULL switches it off. */
+int lumi_set_record_output(lumi_engine* e, float* device_records);
 void* lumi_stream(lumi_engine* e);            /* cudaStream_t the engine launches on */
 int lumi_synchronize(lumi_engine* e);
 /* Kernels launched by the last lumi_predict (our own kernels, for bench.py's gpu_launches). */

@@ -63,7 +63,13 @@ def build_library(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=6) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    # -cudart shared: ONE CUDA runtime per process.  Under Python the library binds to the libcudart.so.12 torch has
+    # already loaded (same SONAME), so the engine and torch share the primary context bookkeeping and tear down in a
+    # defined order at interpreter exit (a second, static runtime needed os._exit in bench.py); the rpath covers
+    # processes that load the library without torch.
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), 'lib64')
+    cmd = ([nvcc, '-shared', '-cudart', 'shared', '-o', LIB] + objs +
+           ['-gencode', 'arch=compute_100a,code=sm_100a', '-Xlinker', '-rpath', '-Xlinker', cuda_lib])
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))

@@ -773,21 +773,29 @@ bool conv_tc_supported(const ConvLayer& L, const ConvIO& io) {
 }
 
 // SMs a persistent conv launch may occupy.  While the engine runs its two-stream pipeline it leaves
-// g_conv_sm_reserve SMs free so the few-CTA latency-bound kernels (sort, NMS scan) of the other half-batch
+// io.sm_reserve SMs free so the few-CTA latency-bound kernels (sort, NMS scan) of the other half-batch
 // run concurrently instead of waiting behind a 148-CTA persistent grid (measured +1.7 % images/s at 8-16).
-int g_conv_sm_reserve = 0;
-static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    LUMI_CUDA_CHECK(cudaGetDevice(&dev));
-    LUMI_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+// The count is cached per DEVICE (an engine may live on any device of the process).
+int device_sm_count() {
+  static int n[LUMI_MAX_DEVICES] = {0};
+  int dev = 0;
+  LUMI_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= LUMI_MAX_DEVICES) {
+    int v = 0;
+    LUMI_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    return v;
   }
-  const int r = g_conv_sm_reserve;
-  return (r > 0 && r < n) ? n - r : n;
+  int v = __atomic_load_n(&n[dev], __ATOMIC_RELAXED);
+  if (!v) {
+    LUMI_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    __atomic_store_n(&n[dev], v, __ATOMIC_RELAXED);
+  }
+  return v;
 }
-
-int g_conv_streamk = 1;            // 0 off, 1 auto (wave-quantisation heuristic), 2 whenever possible
+static int sm_budget(int reserve) {
+  const int n = device_sm_count();
+  return (reserve > 0 && reserve < n) ? n - reserve : n;
+}
 
 void conv_workspace_create(ConvWorkspace& w) {
   int dev = 0, n = 0;
@@ -805,20 +813,23 @@ void conv_workspace_free(ConvWorkspace& w) {
 }
 
 template <int BN, int STAGES, bool RES>
-static void launch_tc_cfg(const TcArgs& a, ConvWorkspace* sk, cudaStream_t st) {
+static void launch_tc_cfg(const TcArgs& a, ConvWorkspace* sk, int streamk, int sm_reserve, cudaStream_t st) {
   using Cfg = TcCfg<BN, STAGES, RES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // cudaFuncSetAttribute is per device: one flag per (kernel instance, device)
+  static bool attr_set[LUMI_MAX_DEVICES] = {false};
+  int dev = 0;
+  LUMI_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= LUMI_MAX_DEVICES || !__atomic_load_n(&attr_set[dev], __ATOMIC_ACQUIRE)) {
     LUMI_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES));
-    attr_set = true;
+    if (dev >= 0 && dev < LUMI_MAX_DEVICES) __atomic_store_n(&attr_set[dev], true, __ATOMIC_RELEASE);
   }
   const long total = (long)a.tiles_w * a.tiles_h * a.tiles_n * a.n_tiles;
-  const int sms = sm_count();
+  const int sms = sm_budget(sm_reserve);
   int grid = (int)(total < sms ? total : sms);                          // persistent: one CTA per SM
   TcArgs args = a;
   args.sk_mode = 0;
-  if (sk && sk->partials && g_conv_streamk > 0 && sms <= sk->ctas) {
+  if (sk && sk->partials && streamk > 0 && sms <= sk->ctas) {
     // stream-K when whole-tile scheduling would leave SMs idle in the last wave (or has fewer tiles than SMs).
     // It balances K iterations, not epilogues, and every CTA pays one partial-tile write and one read: measured
     // (profiles/r1_streamk_per_layer.txt) it wins 13-26 % on the long-K layers (3x3 with C_in >= 128,
@@ -827,7 +838,7 @@ static void launch_tc_cfg(const TcArgs& a, ConvWorkspace* sk, cudaStream_t st) {
     const double waves = (double)total / sms;
     const double eff = waves / std::ceil(waves);
     const long units_per_cta = total * n_iters / sms;
-    const bool forced = g_conv_streamk >= 2 && units_per_cta >= 3;
+    const bool forced = streamk >= 2 && units_per_cta >= 3;
     if (forced || (eff < 0.92 && n_iters >= 12 && units_per_cta >= 12)) {
       args.sk_mode = 1;
       args.sk_partials = sk->partials;
@@ -875,11 +886,11 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   if (res_tma) {          // residual tile prefetched by TMA (box over the unit's input, subsampled by res_stride)
     a.tm_r_hi = cached_out_map(io.res.hi, io.res.n, io.res.h, io.res.w, io.res.c, nb, th, tw, io.res_stride);
     a.tm_r_lo = cached_out_map(io.res.lo, io.res.n, io.res.h, io.res.w, io.res.c, nb, th, tw, io.res_stride);
-    launch_tc_cfg<128, 2, true>(a, io.sk, st);
+    launch_tc_cfg<128, 2, true>(a, io.sk, io.streamk, io.sm_reserve, st);
   } else if (bn == 128) {
-    launch_tc_cfg<128, 3, false>(a, io.sk, st);
+    launch_tc_cfg<128, 3, false>(a, io.sk, io.streamk, io.sm_reserve, st);
   } else {
-    launch_tc_cfg<64, 4, false>(a, io.sk, st);
+    launch_tc_cfg<64, 4, false>(a, io.sk, io.streamk, io.sm_reserve, st);
   }
 }
 

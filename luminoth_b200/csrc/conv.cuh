@@ -32,7 +32,10 @@ struct ConvWorkspace {
 };
 void conv_workspace_create(ConvWorkspace& w);
 void conv_workspace_free(ConvWorkspace& w);
-extern int g_conv_streamk;        // 0 off, 1 auto (default), 2 whenever possible
+// Per-device facts (SM count, opt-in dynamic shared memory of a kernel) are cached per CUDA device, never per
+// process: two engines on two devices, or on two threads, share no mutable launch state.
+int device_sm_count();            // SMs of the CURRENT device
+constexpr int LUMI_MAX_DEVICES = 64;
 
 struct ConvIO {
   Act in;
@@ -44,6 +47,8 @@ struct ConvIO {
   int ho = 0, wo = 0;
   int* overflow_flag = nullptr;
   ConvWorkspace* sk = nullptr;  // enables stream-K scheduling on the tcgen05 path (nullptr: whole tiles only)
+  int streamk = 1;              // stream-K policy of THIS launch: 0 off, 1 auto (wave-quantisation heuristic), 2 whenever possible
+  int sm_reserve = 0;           // SMs a persistent launch leaves free (the engine's two-stream pipeline sets 8)
   // Optional strided ("Toeplitz") view of the input for the tcgen05 path: element pitches between
   // consecutive pixels / rows / images (0 = dense NHWC).  Used by the space-to-depth stem, where each
   // A row is the 64 contiguous fp16 of four horizontally adjacent 16-channel pixels.
@@ -54,7 +59,6 @@ struct ConvIO {
 void conv_layer_upload(ConvLayer& L, const float* w_host, const float* scale_host, const float* bias_host);
 void conv_layer_free(ConvLayer& L);
 
-extern int g_conv_sm_reserve;     // SMs left free by persistent conv launches (set by the engine's pipeline)
 bool conv_tc_supported(const ConvLayer& L, const ConvIO& io);
 void launch_conv_simt(const ConvLayer& L, const ConvIO& io, cudaStream_t st);
 void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st);

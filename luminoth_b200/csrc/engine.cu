@@ -117,6 +117,7 @@ struct lumi_engine {
   uint8_t* d_images = nullptr; size_t images_cap = 0;
   float* d_boxes = nullptr; float* d_scores = nullptr; int* d_labels = nullptr; int* d_counts = nullptr;
   int* d_prop_counts = nullptr;
+  float* d_records = nullptr;   // caller-owned device buffer [max_batch][1 + 6*kmax] (lumi_set_record_output) or null
   std::map<std::string, Tap> taps;
   int planned_n = 0, planned_h = 0, planned_w = 0;
   // per-category device timing (CUDA events on the engine stream), for bench.py's roofline
@@ -540,6 +541,7 @@ struct Ctx {
   ConvWorkspace* sk = nullptr;  // stream-K scratch of this stream
   bool taps = true;             // record debug taps (first half only)
   bool img_f32 = false;         // input pixels are float32 (resized images) instead of uint8
+  int sm_reserve = 0;           // SMs the persistent conv launches of this forward leave to the other stream
   Act act(int n, int h, int w, int c) {
     Act a; a.n = n; a.h = h; a.w = w; a.c = c;
     const size_t bytes = a.numel() * sizeof(__half);
@@ -617,6 +619,8 @@ Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* re
   if (view_pitch) { io.in_pix_pitch = view_pitch[0]; io.in_row_pitch = view_pitch[1]; io.in_img_pitch = view_pitch[2]; }
   io.overflow_flag = cx.e->d_overflow;
   io.sk = cx.sk;
+  io.streamk = cx.e->conv_streamk;
+  io.sm_reserve = cx.sm_reserve;
   if (!cx.dry) {
     const bool tc = cx.e->conv_impl == 1 && conv_tc_supported(L, io);
     const double flops = algorithmic_flops >= 0 ? algorithmic_flops
@@ -671,6 +675,7 @@ void forward_frcnn(Ctx& cx, const void* images, int n, int h, int w) {
   float* out_scores = e->d_scores + (size_t)io * e->kmax;
   int* out_labels = e->d_labels + (size_t)io * e->kmax;
   int* out_counts = e->d_counts + io;
+  float* out_records = e->d_records ? e->d_records + (size_t)io * (1 + 6 * (size_t)e->kmax) : nullptr;
   const std::string root = "truncated_base_network/" + e->arch;
   const int* units = e->arch == "resnet_v1_50" ? RESNET_UNITS_50 : RESNET_UNITS_101;
   Act x;
@@ -739,6 +744,7 @@ void forward_frcnn(Ctx& cx, const void* images, int n, int h, int w) {
                                       cx.st));
       LUMI_CUDA_CHECK(cudaMemsetAsync(out_labels, 0, (size_t)n * post * sizeof(int), cx.st));
       LUMI_CUDA_CHECK(cudaMemcpyAsync(out_counts, prop_counts, n * sizeof(int), cudaMemcpyDeviceToDevice, cx.st));
+      if (out_records) launch_pack_records(out_boxes, out_scores, out_labels, out_counts, n, e->kmax, out_records, cx.st);
     }
     return;
   }
@@ -791,7 +797,7 @@ void forward_frcnn(Ctx& cx, const void* images, int n, int h, int w) {
     ProfScope ps(cx.e, cx.dry, PC_DET_POST);
     NmsWorkspace wsd = ws_view(e->ws_det, io * C);
     launch_class_detections(proposals, (long)post * 4, prop_counts, fc + (C + 1), cls_prob, n, dp, wsd, cx.final_keys,
-                            out_boxes, out_labels, out_scores, out_counts, cx.st);
+                            out_boxes, out_labels, out_scores, out_counts, cx.st, out_records);
   }
 }
 
@@ -931,7 +937,8 @@ void forward_ssd(Ctx& cx, const void* images, int n, int h, int w) {
     NmsWorkspace wsd = ws_view(e->ws_det, io * e->num_classes);
     launch_class_detections(e->d_ssd_anchors, 0, nullptr, loc, prob, n, dp, wsd, cx.final_keys,
                             e->d_boxes + (size_t)io * e->kmax * 4, e->d_labels + (size_t)io * e->kmax,
-                            e->d_scores + (size_t)io * e->kmax, e->d_counts + io, cx.st);
+                            e->d_scores + (size_t)io * e->kmax, e->d_counts + io, cx.st,
+                            e->d_records ? e->d_records + (size_t)io * (1 + 6 * (size_t)e->kmax) : nullptr);
   }
 }
 
@@ -961,6 +968,21 @@ void ensure_arena(lumi_engine* e, Arena& a, size_t need_bytes) {
   a.base = nullptr; a.cap = 0;
   LUMI_CUDA_CHECK(cudaMalloc(&a.base, need_bytes));
   a.cap = need_bytes;
+}
+
+// max_h x max_w at lumi_create is a sizing HINT, not a limit: the reference's resize_image multiplies its up- and
+// down-scale factors (utils/image.py:66-86), so e.g. a 300x600 input becomes 600x1200 -- beyond max_size.  The
+// RPN workspace (the only buffer sized by the image) grows on demand; arenas are re-planned per shape anyway.
+void ensure_image_capacity(lumi_engine* e, int h, int w) {
+  if (e->type != "fasterrcnn") return;                 // SSD runs at its configured fixed size only
+  const long na = (long)cdiv(h, 16) * cdiv(w, 16) * e->A;
+  LUMI_REQUIRE(na < (1L << 30), "lumi_predict: image too large");
+  if (na <= e->ws_rpn.cap) return;
+  LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  if (e->stream2) LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream2));
+  nms_workspace_free(e->ws_rpn);
+  nms_workspace_alloc(e->ws_rpn, e->max_batch, (int)na, e->rpn.post_nms_top_n, std::min((int)na, e->rpn.pre_nms_top_n));
+  e->max_h = std::max(e->max_h, h); e->max_w = std::max(e->max_w, w);
 }
 
 int fail(lumi_engine* e, const Error& err) {
@@ -1109,8 +1131,9 @@ static int predict_impl(lumi_engine* e, const void* images, int esz, int images_
   if (!e->finalized) throw Error(LUMI_ESTATE, "lumi_predict before lumi_finalize");
   LUMI_REQUIRE(images && boxes && scores && labels && counts, "lumi_predict: null buffer");
   LUMI_REQUIRE(n > 0 && n <= e->max_batch, "lumi_predict: batch size exceeds max_batch");
-  LUMI_REQUIRE(h > 0 && w > 0 && h <= e->max_h && w <= e->max_w, "lumi_predict: image larger than max_h x max_w");
+  LUMI_REQUIRE(h > 0 && w > 0, "lumi_predict: empty image");
   LUMI_CUDA_CHECK(cudaSetDevice(e->device));
+  ensure_image_capacity(e, h, w);
   // software pipelining: two half-batches on two streams (off while profiling / tapping intermediates)
   const bool piped = e->pipeline && n >= 2 && !e->profile && !e->debug_taps && e->stream2 != nullptr;
   const int nA = piped ? (n + 1) / 2 : n, nB = n - nA;
@@ -1140,14 +1163,14 @@ static int predict_impl(lumi_engine* e, const void* images, int esz, int images_
   if (e->type == "fasterrcnn") ensure_frcnn_anchors(e, h, w, e->stream);
   Ctx cx = make_ctx(e, false, 0);
   cx.img_f32 = esz == 4;
-  g_conv_sm_reserve = piped ? 8 : 0;
-  g_conv_streamk = e->conv_streamk;
+  cx.sm_reserve = piped ? 8 : 0;
   if (piped) {
     LUMI_CUDA_CHECK(cudaEventRecord(e->ev_fork, e->stream));
     LUMI_CUDA_CHECK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
     Ctx cb = make_ctx(e, false, 1);
     cb.img_off = nA;
     cb.img_f32 = cx.img_f32;
+    cb.sm_reserve = cx.sm_reserve;
     // each half uploads its own images on its own stream: the second half's H2D overlaps the first half's kernels
     if (!images_on_device) {
       LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_images, images, bytes_a, cudaMemcpyHostToDevice, e->stream));
@@ -1194,6 +1217,12 @@ int lumi_predict_f32(lumi_engine* e, const float* images, int images_on_device, 
 }
 
 int lumi_max_detections(lumi_engine* e) { return e ? e->kmax : 0; }
+
+int lumi_set_record_output(lumi_engine* e, float* device_records) {
+  if (!e) return LUMI_EINVAL;
+  e->d_records = device_records;
+  return LUMI_OK;
+}
 void* lumi_stream(lumi_engine* e) { return e ? (void*)e->stream : nullptr; }
 
 int lumi_synchronize(lumi_engine* e) {

@@ -73,7 +73,10 @@ size_t det_final_scratch_bytes(int nimg, int nc, int class_max);   // size of `f
 // boxes_in [nimg][r][4] (or shared anchors when boxes_img_stride == 0), row_counts [nimg] or nullptr
 void launch_class_detections(const float* boxes_in, long boxes_img_stride, const int* row_counts, const float* deltas,
                              const float* cls_prob, int nimg, const DetParams& p, NmsWorkspace& ws, float* final_keys,
-                             float* objects, int* labels, float* probs, int* counts, cudaStream_t st);
+                             float* objects, int* labels, float* probs, int* counts, cudaStream_t st,
+                             float* records = nullptr /* optional packed rows [nimg][1 + 6*total_max], see postproc.cu */);
+void launch_pack_records(const float* boxes, const float* scores, const int* labels, const int* counts, int nimg,
+                         int kmax, float* records, cudaStream_t st);
 
 void launch_sort_desc(const float* scores, int n, int* idx_out, NmsWorkspace& ws, cudaStream_t st);
 void launch_nms_sorted(const float* boxes_sorted, int n, float thr, int max_out, NmsWorkspace& ws, int* keep,

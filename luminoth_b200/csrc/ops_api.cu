@@ -85,17 +85,13 @@ int lumi_op_conv2d(const float* x, int n, int h, int w, int cin, const float* wg
     LUMI_REQUIRE(conv_tc_supported(L, io), "conv2d: this layer shape is not handled by the tensor-core kernel");
     ConvWorkspace sk;
     struct SkGuard { ConvWorkspace& w; ~SkGuard() { conv_workspace_free(w); } } skg{sk};
-    const int saved = g_conv_streamk;
     if (impl == 2) {
       conv_workspace_create(sk);
       io.sk = &sk;
-      g_conv_streamk = 2;
+      io.streamk = 2;
     }
-    try {
-      launch_conv_tc(L, io, st);
-      LUMI_CUDA_CHECK(cudaStreamSynchronize(st));
-    } catch (...) { g_conv_streamk = saved; throw; }
-    g_conv_streamk = saved;
+    launch_conv_tc(L, io, st);
+    LUMI_CUDA_CHECK(cudaStreamSynchronize(st));
   } else {
     launch_conv_simt(L, io, st);
   }

@@ -534,11 +534,13 @@ static void run_nms(NmsWorkspace& ws, int problems, float thr, int max_out, cuda
   LUMI_CUDA_CHECK(cudaGetLastError());
   const size_t staged_smem = ((size_t)ws.words + 2 * 64 * (size_t)ws.words) * sizeof(unsigned long long);
   if (staged_smem <= 200 * 1024) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};        // cudaFuncSetAttribute is per device
+    int dev = 0;
+    LUMI_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !__atomic_load_n(&attr[dev], __ATOMIC_ACQUIRE)) {
       LUMI_CUDA_CHECK(cudaFuncSetAttribute(nms_scan_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            200 * 1024));
-      attr = true;
+      if (dev >= 0 && dev < 64) __atomic_store_n(&attr[dev], true, __ATOMIC_RELEASE);
     }
     nms_scan_staged_kernel<<<problems, 256, staged_smem, st>>>(ws.mask, ws.nvalid, ws.ncap, ws.words, max_out, ws.keep,
                                                               ws.nkeep);
@@ -677,11 +679,13 @@ __global__ void det_output_kernel(const float* __restrict__ sboxes, const float*
                                   const int* __restrict__ keep, const int* __restrict__ forder,
                                   const int* __restrict__ fnvalid, int nc, int cap, int class_max, int total_max,
                                   float* __restrict__ objects, int* __restrict__ labels, float* __restrict__ probs,
-                                  int* __restrict__ counts) {
+                                  int* __restrict__ counts, float* __restrict__ records) {
   const int img = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int nv = fnvalid[img];
-  if (k == 0) counts[img] = nv;
+  // optional packed all-gather record of this image: {count, boxes[K][4], scores[K], labels[K]} as float32
+  float* rec = records ? records + (size_t)img * (1 + 6 * (size_t)total_max) : nullptr;
+  if (k == 0) { counts[img] = nv; if (rec) rec[0] = (float)nv; }
   if (k >= total_max) return;
   float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
   float s = 0.f;
@@ -698,13 +702,44 @@ __global__ void det_output_kernel(const float* __restrict__ sboxes, const float*
   reinterpret_cast<float4*>(objects)[(size_t)img * total_max + k] = b;
   probs[(size_t)img * total_max + k] = s;
   labels[(size_t)img * total_max + k] = lab;
+  if (rec) {
+    float* rb = rec + 1 + 4 * (size_t)k;
+    rb[0] = b.x; rb[1] = b.y; rb[2] = b.z; rb[3] = b.w;
+    rec[1 + 4 * (size_t)total_max + k] = s;
+    rec[1 + 5 * (size_t)total_max + k] = (float)lab;
+  }
+}
+
+// records of the RPN-only mode (predicting.py:85-92: objects = proposals, labels = 0) and of any caller that has
+// plain (boxes, scores, labels, counts) arrays: same layout as det_output_kernel writes.
+__global__ void pack_records_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                                    const int* __restrict__ labels, const int* __restrict__ counts, int kmax,
+                                    float* __restrict__ records) {
+  const int img = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  float* rec = records + (size_t)img * (1 + 6 * (size_t)kmax);
+  if (k == 0) rec[0] = (float)counts[img];
+  if (k >= kmax) return;
+  const float4 b = reinterpret_cast<const float4*>(boxes)[(size_t)img * kmax + k];
+  float* rb = rec + 1 + 4 * (size_t)k;
+  rb[0] = b.x; rb[1] = b.y; rb[2] = b.z; rb[3] = b.w;
+  rec[1 + 4 * (size_t)kmax + k] = scores[(size_t)img * kmax + k];
+  rec[1 + 5 * (size_t)kmax + k] = (float)labels[(size_t)img * kmax + k];
+}
+void launch_pack_records(const float* boxes, const float* scores, const int* labels, const int* counts, int nimg,
+                         int kmax, float* records, cudaStream_t st) {
+  if (!nimg || !kmax) return;
+  dim3 g(cdiv(kmax, 128), nimg);
+  pack_records_kernel<<<g, 128, 0, st>>>(boxes, scores, labels, counts, kmax, records);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
 }
 
 // final_keys: scratch of det_final_scratch_bytes(): [nimg][nc*class_max] float keys, int order [same],
 // int nvalid[nimg], then the radix ping-pong buffers
 void launch_class_detections(const float* boxes_in, long boxes_img_stride, const int* row_counts, const float* deltas,
                              const float* cls_prob, int nimg, const DetParams& p, NmsWorkspace& ws, float* final_keys,
-                             float* objects, int* labels, float* probs, int* counts, cudaStream_t st) {
+                             float* objects, int* labels, float* probs, int* counts, cudaStream_t st, float* records) {
   const int P = nimg * p.nc;
   LUMI_REQUIRE(P <= ws.problems && p.r <= ws.cap && p.class_max == ws.max_out, "class_detections: workspace mismatch");
   if (!P || !p.r) return;
@@ -736,7 +771,7 @@ void launch_class_detections(const float* boxes_in, long boxes_img_stride, const
   run_sort(fkeys, nimg, fcap, fcap, nullptr, p.total_max, forder, fnvalid, fscratch, st);
   dim3 g4(cdiv(p.total_max, 128), nimg);
   det_output_kernel<<<g4, 128, 0, st>>>(ws.sboxes, ws.sscores, ws.keep, forder, fnvalid, p.nc, ws.ncap, p.class_max,
-                                        p.total_max, objects, labels, probs, counts);
+                                        p.total_max, objects, labels, probs, counts, records);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }

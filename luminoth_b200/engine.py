@@ -41,6 +41,7 @@ SIGNATURES = {
     'lumi_predict_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     'lumi_max_detections': (ctypes.c_int, [ctypes.c_void_p]),
+    'lumi_set_record_output': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'lumi_stream': (ctypes.c_void_p, [ctypes.c_void_p]),
     'lumi_synchronize': (ctypes.c_int, [ctypes.c_void_p]),
     'lumi_last_launch_count': (ctypes.c_int, [ctypes.c_void_p]),
@@ -229,6 +230,14 @@ class Engine(object):
                                         ctypes.c_void_p(labels.data_ptr()), ctypes.c_void_p(counts.data_ptr()), 1)
             if rc != LUMI_OK:
                 _raise(rc, self._lib.lumi_last_error(self._h))
+
+    def set_record_output(self, records):
+        """CUDA float32 tensor [max_batch, 1 + 6*K] (or None): every following predict also writes one packed
+        {count, boxes, scores, labels} row per image there -- the send buffer of the detection all-gather."""
+        if records is not None:
+            assert records.is_cuda and records.is_contiguous() and records.numel() >= self.max_batch * (1 + 6 * self.max_detections)
+        self._records = records          # keep the buffer alive
+        self._lib.lumi_set_record_output(self._h, ctypes.c_void_p(records.data_ptr() if records is not None else 0))
 
     def set_pipeline(self, enable=True):
         self._lib.lumi_set_pipeline(self._h, int(bool(enable)))

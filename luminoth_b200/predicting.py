@@ -6,10 +6,13 @@ rounded to 4 decimals).  ``predict_batch(images)`` is the batched extension
 (the reference is hard-wired to batch 1, ``fasterrcnn.py:101-103``).
 
 What changed underneath: graph build + ``session.run`` is one call into the
-sm_100a engine (``lumi_predict``).  The aspect-preserving resize of
-``datasets/object_detection_dataset.py:71-83`` / ``utils/image.py:38-147`` is
-still done on the host here (SURVEY section 8f item 2 moves it to the GPU);
-it is the identity at the benchmark shapes.
+sm_100a engine (``lumi_predict`` / ``lumi_predict_f32``).  The aspect-preserving
+resize of ``datasets/object_detection_dataset.py:71-83`` / ``utils/image.py:38-147``
+runs on the GPU (``lumi_op_resize_bilinear``, bit-identical to the TF1 legacy
+bilinear kernel); only its size arithmetic (float32, like the reference) stays on
+the host.  Images of different sizes in one ``predict_batch`` call are bucketed by
+their preprocessed size, each bucket runs as one batched engine call, and the
+results come back in the caller's order.
 """
 import json
 import math
@@ -103,7 +106,7 @@ def load_checkpoint_weights(engine, job_dir):
         if tuple(reader.shape(name)) != tuple(shape):
             raise ValueError("checkpoint variable '%s' has shape %s, the model expects %s"
                              % (name, tuple(reader.shape(name)), tuple(shape)))
-        weights[name] = reader.get_tensor(name).astype(np.float32, copy=False)
+        weights[name] = reader.get_tensor(name, verify=True).astype(np.float32, copy=False)   # per-tensor crc32c checked
     if missing:
         raise ValueError('checkpoint %s lacks %d model variables, e.g. %s' % (prefix, len(missing), missing[:3]))
     return weights
@@ -148,28 +151,34 @@ class PredictorNetwork(object):
 
     # -- batched extension
     def predict_batch(self, images):
+        """Predictions for a list of (H, W, 3) images of ANY mix of sizes, in the caller's order.  Images are grouped
+        by the size the preprocessing gives them (``target_size``); each group runs through the engine in chunks of
+        ``max_batch`` -- a directory of equally sized frames (``predict.py:69-97``, video frames ``:100-171``) is
+        one batched call per chunk instead of one call per image."""
         images = [np.asarray(im) for im in images]
+        if not images:
+            return []
         for im in images:
             if im.ndim != 3 or im.shape[2] != 3:
                 raise ValueError('expected an (H, W, 3) RGB image')
         sizes = [target_size(im.shape, self.config) for im in images]
-        if len({(nh, nw) for nh, nw, _ in sizes}) != 1:
-            raise ValueError('predict_batch needs images that preprocess to one size; got %s'
-                             % sorted({(nh, nw) for nh, nw, _ in sizes}))
-        nh, nw = sizes[0][0], sizes[0][1]
-        untouched = all(im.dtype == np.uint8 and im.shape[:2] == (nh, nw) for im in images)
-        out = []
-        for s in range(0, len(images), self.engine.max_batch):
-            chunk = images[s:s + self.engine.max_batch]
-            if untouched:       # integer pixels, no resize: the uint8 entry point (the benchmark shapes)
-                batch = np.stack(chunk)
-            else:               # the reference feeds the resized FLOAT image (predicting.py:110-112)
-                batch = self._resize_on_device(chunk, nh, nw)
-            boxes, scores, labels, counts = self.engine.predict_raw(batch)
-            for i in range(len(chunk)):
-                k = int(counts[i])
-                out.append(format_predictions(boxes[i, :k], labels[i, :k], scores[i, :k], sizes[s + i][2],
-                                              self.class_labels))
+        buckets = {}                                     # (nh, nw) -> indices, first-seen order
+        for i, (nh, nw, _) in enumerate(sizes):
+            buckets.setdefault((nh, nw), []).append(i)
+        out = [None] * len(images)
+        for (nh, nw), idxs in buckets.items():
+            untouched = all(images[i].dtype == np.uint8 and images[i].shape[:2] == (nh, nw) for i in idxs)
+            for s in range(0, len(idxs), self.engine.max_batch):
+                chunk = idxs[s:s + self.engine.max_batch]
+                if untouched:   # integer pixels, no resize: the uint8 entry point (the benchmark shapes)
+                    batch = np.stack([images[i] for i in chunk])
+                else:           # the reference feeds the resized FLOAT image (predicting.py:110-112)
+                    batch = self._resize_on_device([images[i] for i in chunk], nh, nw)
+                boxes, scores, labels, counts = self.engine.predict_raw(batch)
+                for j, i in enumerate(chunk):
+                    k = int(counts[j])
+                    out[i] = format_predictions(boxes[j, :k], labels[j, :k], scores[j, :k], sizes[i][2],
+                                                self.class_labels)
         return out
 
     def _resize_on_device(self, images, nh, nw):

@@ -1,0 +1,28 @@
+#!/bin/bash
+# Round 2, call A: full GPU test suite (incl. the BASELINE-config parity tests), clean-exit check of bench.py,
+# bench lines for the three workloads, one-step ncu --set full for SSD and R101 (r1 only had R50).
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/a_smi.txt 2>&1
+timeout -s KILL 1500 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/a_pytest_gpu.log 2>&1
+echo "pytest gpu exit $?" > gpurun_out/a_summary.txt
+timeout -s KILL 600 python bench.py --steps 20 --warmup 3 --layers --no-cpu-baseline > gpurun_out/a_bench_r50.json 2> gpurun_out/a_bench_r50.err
+echo "bench r50 exit $? (must be 0: normal interpreter exit, no os._exit)" >> gpurun_out/a_summary.txt
+timeout -s KILL 600 python bench.py --workload ssd --steps 20 --warmup 3 --layers --no-cpu-baseline > gpurun_out/a_bench_ssd.json 2> gpurun_out/a_bench_ssd.err
+echo "bench ssd exit $?" >> gpurun_out/a_summary.txt
+timeout -s KILL 600 python bench.py --workload frcnn_r101 --steps 10 --warmup 3 --layers --no-cpu-baseline > gpurun_out/a_bench_r101.json 2> gpurun_out/a_bench_r101.err
+echo "bench r101 exit $?" >> gpurun_out/a_summary.txt
+for wl in ssd frcnn_r101; do
+  timeout -s KILL 1200 ncu --set full --clock-control none --profile-from-start off -f -o /tmp/ncu_$wl python bench.py --workload $wl --ncu-range --ncu-unpiped --no-cpu-baseline > gpurun_out/a_ncu_$wl.log 2>&1
+  echo "ncu $wl exit $?" >> gpurun_out/a_summary.txt
+  python scripts/ncu_step_summary.py /tmp/ncu_$wl.ncu-rep $wl gpurun_out/a_ncu_$wl > gpurun_out/a_ncu_${wl}_summary.txt 2>&1
+done
+tail -n 15 gpurun_out/a_pytest_gpu.log
+cat gpurun_out/a_summary.txt
+python - <<'PY'
+import json
+for wl in ('r50','ssd','r101'):
+    try:
+        d=json.load(open('gpurun_out/a_bench_%s.json'%wl)); print(wl, d['value'], d['ms_per_step'], d['e2e']['value'], d['category_ms_per_step'], d['roofline']['frac'])
+    except Exception as e: print(wl, 'ERR', e)
+PY
+cat gpurun_out/parity_report_baseline.json 2>/dev/null | head -120

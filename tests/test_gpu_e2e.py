@@ -291,8 +291,9 @@ def test_stream_k_schedule_is_result_neutral():
 
 def test_engine_capacity_is_not_part_of_the_result():
     """An engine created for (max_batch 4, 256x384) must give, for a smaller batch of smaller images, exactly
-    what a tightly sized engine gives (ragged use of one handle: predicting.py serves images of any size);
-    an image beyond the planned maximum is refused, not truncated."""
+    what a tightly sized engine gives (ragged use of one handle: predicting.py serves images of any size).
+    max_h x max_w is a sizing hint: an image beyond it grows the workspace instead of being refused (the
+    reference's resize can exceed max_size, utils/image.py:66-86) and still gives the tight engine's result."""
     cfg = frcnn_cfg('resnet_v1_50')
     wts = synth.make_weights(cfg, seed=7)
     imgs = synth.make_images(1, 160, 224, seed=8)
@@ -309,9 +310,50 @@ def test_engine_capacity_is_not_part_of_the_result():
     big.predict_raw(other)
     for x, y in zip(big.predict_raw(imgs), a):
         np.testing.assert_array_equal(x, y)
-    with pytest.raises((ValueError, RuntimeError)):
-        big.predict_raw(synth.make_images(1, 300, 400, seed=1))        # larger than the planned maximum
-    big.close(); tight.close()
+    larger = synth.make_images(1, 300, 400, seed=1)                    # larger than the planned maximum
+    tight2 = Engine(cfg, max_batch=1, max_h=300, max_w=400)
+    tight2.load_weights(wts).finalize()
+    for x, y in zip(big.predict_raw(larger), tight2.predict_raw(larger)):
+        np.testing.assert_array_equal(x[:1], y[:1])
+    for x, y in zip(big.predict_raw(imgs), a):                         # and the grown engine still serves the small one
+        np.testing.assert_array_equal(x, y)
+    big.close(); tight.close(); tight2.close()
+
+
+def test_predictor_network_wide_image_beyond_max_size():
+    """a 300x600 input is resized to 600x1200 (the reference multiplies its up- and down-scale factors,
+    utils/image.py:66-86), wider than max_size 1024: PredictorNetwork must serve it like the reference does."""
+    cfg = frcnn_cfg('resnet_v1_50')
+    wts = synth.make_weights(cfg, seed=7)
+    img = synth.make_images(1, 300, 600, seed=31)[0]
+    net = PredictorNetwork(cfg, weights=wts)
+    got = net.predict_image(img)
+    ref = opredict.predict_image(img, wts, cfg)
+    assert len(got) == len(ref) and len(got) > 0
+    free = list(ref)
+    for g in got:
+        hit = [r for r in free if r['label'] == g['label'] and abs(r['prob'] - g['prob']) <= 1.01e-4
+               and max(abs(a - b) for a, b in zip(g['bbox'], r['bbox'])) <= 1]
+        assert hit, 'no reference detection for %r' % (g,)
+        free.remove(hit[0])
+    net.engine.close()
+
+
+def test_predict_batch_mixed_sizes_keeps_order():
+    """predict_batch buckets images by preprocessed size and returns results in the caller's order; every
+    entry equals the single-image call (images are independent units)."""
+    cfg = frcnn_cfg('resnet_v1_50')
+    wts = synth.make_weights(cfg, seed=7)
+    a = synth.make_images(2, 600, 640, seed=41)
+    b = synth.make_images(2, 375, 500, seed=42)
+    order = [a[0], b[0], a[1], b[1]]
+    net = PredictorNetwork(cfg, weights=wts, max_batch=2)
+    assert net.predict_batch([]) == []
+    net.engine.set_conv_streamk('off')                 # batch-size independent bits (stream-K split points depend on the batch)
+    got = net.predict_batch(order)
+    single = [net.predict_image(im) for im in order]
+    assert got == single and all(len(g) > 0 for g in got)
+    net.engine.close()
 
 
 def test_predictor_network_restores_a_saver_v2_checkpoint(tmp_path):

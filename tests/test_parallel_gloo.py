@@ -40,9 +40,21 @@ def _worker(rank, world, port, q):
     rec = torch.zeros((Bmax, P.record_width(K)))
     rec[:B] = P.pack_detections(boxes, scores, labels, counts)
     allrec = P.all_gather_detections(rec)
-    b2, s2, l2, c2 = P.unpack_detections(allrec[rank * Bmax:rank * Bmax + B], K)
-    ok = ok and torch.equal(b2, boxes) and torch.equal(s2, scores) and torch.equal(l2, labels) and torch.equal(c2, counts)
     ok = ok and allrec.shape == (world * Bmax, P.record_width(K))
+    # EVERY rank's slice must hold that rank's detections: regenerate what rank r packed (same seeded generator)
+    # and compare slice r of the gathered tensor with it -- the own slice and, crucially, the peers' slices
+    for r in range(world):
+        lo_r, hi_r = P.shard_range(11, r, world)
+        Br = hi_r - lo_r
+        gr = torch.Generator().manual_seed(100 + r)
+        boxes_r = torch.rand((Br, K, 4), generator=gr); scores_r = torch.rand((Br, K), generator=gr)
+        labels_r = torch.randint(0, 80, (Br, K), generator=gr, dtype=torch.int32)
+        counts_r = torch.randint(0, K + 1, (Br,), generator=gr, dtype=torch.int32)
+        b2, s2, l2, c2 = P.unpack_detections(allrec[r * Bmax:r * Bmax + Br], K)
+        ok = ok and torch.equal(b2, boxes_r) and torch.equal(s2, scores_r) and torch.equal(l2, labels_r)
+        ok = ok and torch.equal(c2, counts_r)
+        ok = ok and bool((allrec[r * Bmax + Br:(r + 1) * Bmax] == 0).all())       # the padding rows stay zero
+    ok = ok and not torch.equal(allrec[:Bmax], allrec[Bmax:])                      # the two slices really differ
     q.put((rank, bool(ok), (lo, hi)))
     dist.destroy_process_group()
 
