@@ -222,6 +222,223 @@ __global__ void __launch_bounds__(32 * NW, (CPL == 8 ? 2 : 3) * (8 / NW)) roi_po
   }
 }
 
+
+// =====================================================================================================================
+// Column-walk kernel (round 2).  One WARP = one ROI x one channel slice (32 lanes x CPL channels); no shared memory,
+// no CTA-level synchronisation.  For each pooled column q the warp walks the 2*oh sample rows top to bottom and keeps
+// the horizontally interpolated values of the last two feature rows it touched in registers (H0 / H1, tagged with
+// their row index): vertically adjacent samples -- inside a cell AND across cells -- reuse them, so each feature row
+// is fetched once per pooled column instead of once per sample row (round-1 kernel: sharing inside one 2x2 cell only).
+// The sample tables live in the lanes of the warp (lane t = sample t) and are broadcast with shuffles; the lerps run
+// on the packed fp32 pipe (FADD2 / FFMA2: two IEEE fp32 results per instruction, each rounded exactly like the scalar
+// op, so parity is unaffected).  Instruction count per ROI and channel: ~3.0 k (round 1) -> ~0.9 k.
+// =====================================================================================================================
+template <int CPL> struct RoiVec { float2 p[CPL / 2]; };
+
+template <int CPL>
+__device__ __forceinline__ RoiVec<CPL> roi_load(const float* f, int off) {
+  RoiVec<CPL> v;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(f + off));
+  v.p[0] = make_float2(a.x, a.y); v.p[1] = make_float2(a.z, a.w);
+  if (CPL == 8) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(f + off) + 1);
+    v.p[CPL / 2 - 2] = make_float2(b.x, b.y); v.p[CPL / 2 - 1] = make_float2(b.z, b.w);
+  }
+  return v;
+}
+// l + (r - l) * t   (TF: top_left + (top_right - top_left) * x_lerp; the multiply-add is contracted like the
+// round-1 kernel and like any -O2 CPU build with FMA)
+template <int CPL>
+__device__ __forceinline__ RoiVec<CPL> roi_lerp(const RoiVec<CPL>& l, const RoiVec<CPL>& r, float t) {
+  RoiVec<CPL> h;
+  const float2 tt = make_float2(t, t);
+#pragma unroll
+  for (int j = 0; j < CPL / 2; ++j)
+    h.p[j] = __ffma2_rn(__fadd2_rn(r.p[j], make_float2(-l.p[j].x, -l.p[j].y)), tt, l.p[j]);
+  return h;
+}
+struct RoiX { int lo, hi; float t; int ok; };   // lo / hi: ELEMENT offsets of the two feature columns (x * C)
+// horizontal interpolation of feature row `rowoff` (element offset of its first pixel) at the two x samples of a
+// pooled column; loads shared between the two samples are issued once (all indices are warp-uniform)
+template <int CPL>
+__device__ __forceinline__ void roi_row(const float* f, int rowoff, const RoiX& s0, const RoiX& s1,
+                                        RoiVec<CPL>& h0, RoiVec<CPL>& h1) {
+  constexpr int c = 1;                                  // offsets are already in elements (32-bit: one IMAD.WIDE per load)
+  const RoiVec<CPL> l0 = roi_load<CPL>(f, rowoff + s0.lo * c);
+  const bool r0_is_l0 = s0.hi == s0.lo;
+  RoiVec<CPL> r0 = l0;
+  if (!r0_is_l0) r0 = roi_load<CPL>(f, rowoff + s0.hi * c);
+  h0 = roi_lerp<CPL>(l0, r0, s0.t);
+  if (s1.lo == s0.lo) {
+    if (s1.hi == s0.hi) h1 = roi_lerp<CPL>(l0, r0, s1.t);
+    else if (s1.hi == s1.lo) h1 = roi_lerp<CPL>(l0, l0, s1.t);
+    else { const RoiVec<CPL> r1 = roi_load<CPL>(f, rowoff + s1.hi * c); h1 = roi_lerp<CPL>(l0, r1, s1.t); }
+  } else if (s1.lo == s0.hi) {
+    if (s1.hi == s1.lo) h1 = roi_lerp<CPL>(r0, r0, s1.t);
+    else { const RoiVec<CPL> r1 = roi_load<CPL>(f, rowoff + s1.hi * c); h1 = roi_lerp<CPL>(r0, r1, s1.t); }
+  } else {
+    const RoiVec<CPL> l1 = roi_load<CPL>(f, rowoff + s1.lo * c);
+    if (s1.hi == s1.lo) h1 = roi_lerp<CPL>(l1, l1, s1.t);
+    else { const RoiVec<CPL> r1 = roi_load<CPL>(f, rowoff + s1.hi * c); h1 = roi_lerp<CPL>(l1, r1, s1.t); }
+  }
+}
+
+template <int CPL>
+__device__ __forceinline__ void roi_max_sample(RoiVec<CPL>& best, const RoiVec<CPL>& top, const RoiVec<CPL>& bot,
+                                               float ly, bool ok) {
+  if (ok) {
+    const RoiVec<CPL> v = roi_lerp<CPL>(top, bot, ly);
+#pragma unroll
+    for (int j = 0; j < CPL / 2; ++j) { best.p[j].x = fmaxf(best.p[j].x, v.p[j].x); best.p[j].y = fmaxf(best.p[j].y, v.p[j].y); }
+  } else {                                              // extrapolation_value = 0
+#pragma unroll
+    for (int j = 0; j < CPL / 2; ++j) { best.p[j].x = fmaxf(best.p[j].x, 0.f); best.p[j].y = fmaxf(best.p[j].y, 0.f); }
+  }
+}
+
+// one sample row: (re)compute the rows that are not resident, then the two bilinear samples of the pooled column.
+// HT / HB are the register sets currently playing "top" / "bottom" (the caller dispatches on the role parity).
+template <int CPL>
+__device__ __forceinline__ void roi_step(const float* f, int rowstride, int ylo, int yhi, float ly, bool need_top,
+                                         bool need_bot, const RoiX& x0, const RoiX& x1, RoiVec<CPL> (&HT)[2],
+                                         RoiVec<CPL> (&HB)[2], RoiVec<CPL>& best) {
+  if (need_top) roi_row<CPL>(f, ylo * rowstride, x0, x1, HT[0], HT[1]);
+  if (need_bot) roi_row<CPL>(f, yhi * rowstride, x0, x1, HB[0], HB[1]);
+  if (yhi == ylo) {
+    roi_max_sample<CPL>(best, HT[0], HT[0], ly, x0.ok != 0);
+    roi_max_sample<CPL>(best, HT[1], HT[1], ly, x1.ok != 0);
+  } else {
+    roi_max_sample<CPL>(best, HT[0], HB[0], ly, x0.ok != 0);
+    roi_max_sample<CPL>(best, HT[1], HB[1], ly, x1.ok != 0);
+  }
+}
+
+template <int CPL, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) roi_pool_cols_kernel(const RoiArgs a) {
+  constexpr int SLICE = 32 * CPL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x;                                   // global roi row = img * rmax + r
+  const int slice = blockIdx.y * WARPS + warp;
+  if (slice * SLICE >= a.c) return;                             // whole warp
+  const int c0 = slice * SLICE + lane * CPL;
+  const bool lane_ok = c0 < a.c;
+  const int img = row / a.rmax, r = row - img * a.rmax;
+  const int oh = a.crop_h >> 1, ow = a.crop_w >> 1;
+  const int ncell = oh * ow;
+  const bool live = (a.counts == nullptr || r < a.counts[img]);
+  if (!live) {                                                  // padded row: zeros (the heads read every row)
+    if (lane_ok) {
+      if (a.ohi)
+        for (int cell = 0; cell < ncell; ++cell) {
+          const size_t off = ((size_t)row * ncell + cell) * a.c + c0;
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) { a.ohi[off + j] = __float2half_rn(0.f); a.olo[off + j] = __float2half_rn(0.f); }
+        }
+      if (a.mhi)
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) { a.mhi[(size_t)row * a.c + c0 + j] = __float2half_rn(0.f); a.mlo[(size_t)row * a.c + c0 + j] = __float2half_rn(0.f); }
+    }
+    return;
+  }
+  // ---- sample table: lane t < crop_h holds y sample t, lanes crop_h .. crop_h+crop_w-1 the x samples (TF
+  // crop_and_resize arithmetic in the reference's operation order; boxes normalised by the IMAGE size, quirk Q3)
+  int s_lo = 0, s_hi = 0, s_ok = 0;
+  float s_t = 0.f;
+  {
+    const int nsamp = a.crop_h + a.crop_w;                      // <= 32 (checked by the launcher)
+    if (lane < nsamp) {
+      const bool is_y = lane < a.crop_h;
+      const int k = is_y ? lane : lane - a.crop_h;
+      const float* rb = a.rois + (size_t)row * 4;
+      const float lo_n = is_y ? __fdiv_rn(rb[1], a.im_h) : __fdiv_rn(rb[0], a.im_w);
+      const float hi_n = is_y ? __fdiv_rn(rb[3], a.im_h) : __fdiv_rn(rb[2], a.im_w);
+      const int crop = is_y ? a.crop_h : a.crop_w;
+      const float Dm1 = (float)((is_y ? a.fh : a.fw) - 1);
+      const float step = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(hi_n, lo_n), Dm1), (float)(crop - 1)) : 0.f;
+      const float in = crop > 1 ? __fadd_rn(__fmul_rn(lo_n, Dm1), __fmul_rn((float)k, step))
+                                : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(lo_n, hi_n)), Dm1);
+      s_ok = !(in < 0.f || in > Dm1);
+      s_lo = s_ok ? (int)floorf(in) : 0;
+      s_hi = s_ok ? (int)ceilf(in) : 0;
+      s_t = __fsub_rn(in, (float)s_lo);
+    }
+  }
+  const float* f = a.fmap + (size_t)img * a.fh * a.fw * a.c + (lane_ok ? c0 : 0);
+  asm volatile("" : "+l"(f));     // keep ONE per-lane base pointer: every tap address is then base + 32-bit offset
+  const int rowstride = a.fw * a.c;
+  RoiVec<CPL> msum;
+#pragma unroll
+  for (int j = 0; j < CPL / 2; ++j) msum.p[j] = make_float2(0.f, 0.f);
+  constexpr unsigned FULL = 0xffffffffu;
+  for (int q = 0; q < ow; ++q) {
+    RoiX x0, x1;
+    const int lx = a.crop_h + 2 * q;
+    x0.lo = __shfl_sync(FULL, s_lo, lx) * a.c; x0.hi = __shfl_sync(FULL, s_hi, lx) * a.c;
+    x0.t = __shfl_sync(FULL, s_t, lx); x0.ok = __shfl_sync(FULL, s_ok, lx);
+    x1.lo = __shfl_sync(FULL, s_lo, lx + 1) * a.c; x1.hi = __shfl_sync(FULL, s_hi, lx + 1) * a.c;
+    x1.t = __shfl_sync(FULL, s_t, lx + 1); x1.ok = __shfl_sync(FULL, s_ok, lx + 1);
+    RoiVec<CPL> H0[2], H1[2];
+#pragma unroll
+    for (int j = 0; j < CPL / 2; ++j) { H0[0].p[j] = H0[1].p[j] = H1[0].p[j] = H1[1].p[j] = make_float2(0.f, 0.f); }
+    int tag_top = -1, tag_bot = -1, parity = 0;               // parity 0: H0 plays "top", H1 "bottom"
+    for (int py = 0; py < oh; ++py) {
+      RoiVec<CPL> best;
+#pragma unroll
+      for (int j = 0; j < CPL / 2; ++j) best.p[j] = make_float2(-INFINITY, -INFINITY);
+#pragma unroll
+      for (int sy = 0; sy < 2; ++sy) {
+        const int i = 2 * py + sy;
+        const int ylo = __shfl_sync(FULL, s_lo, i), yhi = __shfl_sync(FULL, s_hi, i);
+        const float ly = __shfl_sync(FULL, s_t, i);
+        const int yok = __shfl_sync(FULL, s_ok, i);
+        if (!yok) {
+#pragma unroll
+          for (int j = 0; j < CPL / 2; ++j) { best.p[j].x = fmaxf(best.p[j].x, 0.f); best.p[j].y = fmaxf(best.p[j].y, 0.f); }
+          continue;
+        }
+        bool need_top = false;
+        if (ylo != tag_top) {
+          if (ylo == tag_bot) { const int t = tag_top; tag_top = tag_bot; tag_bot = t; parity ^= 1; }
+          else { need_top = true; tag_top = ylo; }
+        }
+        const bool need_bot = (yhi != ylo) && (yhi != tag_bot);
+        if (need_bot) tag_bot = yhi;
+        if (parity == 0) roi_step<CPL>(f, rowstride, ylo, yhi, ly, need_top, need_bot, x0, x1, H0, H1, best);
+        else             roi_step<CPL>(f, rowstride, ylo, yhi, ly, need_top, need_bot, x0, x1, H1, H0, best);
+      }
+#pragma unroll
+      for (int j = 0; j < CPL / 2; ++j) { msum.p[j].x += best.p[j].x; msum.p[j].y += best.p[j].y; }
+      if (a.ohi && lane_ok) {
+        const size_t off = ((size_t)row * ncell + (size_t)py * ow + q) * a.c + c0;
+        __half2 vh[CPL / 2], vl[CPL / 2];
+#pragma unroll
+        for (int j = 0; j < CPL / 2; ++j) split2_f32(best.p[j].x, best.p[j].y, vh[j], vl[j]);
+        if (CPL == 8) {
+          *reinterpret_cast<uint4*>(a.ohi + off) = *reinterpret_cast<const uint4*>(vh);
+          *reinterpret_cast<uint4*>(a.olo + off) = *reinterpret_cast<const uint4*>(vl);
+        } else {
+          *reinterpret_cast<uint2*>(a.ohi + off) = *reinterpret_cast<const uint2*>(vh);
+          *reinterpret_cast<uint2*>(a.olo + off) = *reinterpret_cast<const uint2*>(vl);
+        }
+      }
+    }
+  }
+  if (a.mhi && lane_ok) {            // fused tf.reduce_mean over the pooled cells (rcnn.py:188)
+    __half2 vh[CPL / 2], vl[CPL / 2];
+#pragma unroll
+    for (int j = 0; j < CPL / 2; ++j)
+      split2_f32(__fdiv_rn(msum.p[j].x, (float)ncell), __fdiv_rn(msum.p[j].y, (float)ncell), vh[j], vl[j]);
+    const size_t off = (size_t)row * a.c + c0;
+    if (CPL == 8) {
+      *reinterpret_cast<uint4*>(a.mhi + off) = *reinterpret_cast<const uint4*>(vh);
+      *reinterpret_cast<uint4*>(a.mlo + off) = *reinterpret_cast<const uint4*>(vl);
+    } else {
+      *reinterpret_cast<uint2*>(a.mhi + off) = *reinterpret_cast<const uint2*>(vh);
+      *reinterpret_cast<uint2*>(a.mlo + off) = *reinterpret_cast<const uint2*>(vl);
+    }
+  }
+}
+
 void launch_roi_pool(const float* fmap_f32, int n, int fh, int fw, int c, const float* rois, const int* counts, int rmax,
                      float im_h, float im_w, int ph, int pw, Act out, Act mean, cudaStream_t st) {
   LUMI_REQUIRE(c % 8 == 0, "roi_pool: C must be a multiple of 8");
@@ -235,6 +452,22 @@ void launch_roi_pool(const float* fmap_f32, int n, int fh, int fw, int c, const 
   LUMI_REQUIRE(out.hi || mean.hi, "roi_pool: no output requested");
   long rows = (long)n * rmax;
   if (!rows) return;
+  // LUMI_ROI_KERNEL: "cols" (default, round-2 column-walk kernel) | "cells" (round-1 kernel, kept for A/B measurement)
+  static const int variant = [] { const char* e = getenv("LUMI_ROI_KERNEL"); return (e && e[0] == 'c' && e[1] == 'e') ? 0 : 1; }();
+  static const int cols_cpl = [] { const char* e = getenv("LUMI_ROI_COLS_CPL"); return (e && atoi(e) == 8) ? 8 : 4; }();
+  if (variant == 1 && a.crop_h + a.crop_w <= 32 && (a.crop_h & 1) == 0 && (a.crop_w & 1) == 0 && c % cols_cpl == 0) {
+    constexpr int W = 4;
+    if (cols_cpl == 8) {
+      dim3 grid((unsigned)rows, (unsigned)cdiv(c, 256 * W));
+      roi_pool_cols_kernel<8, W><<<grid, 32 * W, 0, st>>>(a);
+    } else {
+      dim3 grid((unsigned)rows, (unsigned)cdiv(c, 128 * W));
+      roi_pool_cols_kernel<4, W><<<grid, 32 * W, 0, st>>>(a);
+    }
+    count_launch();
+    LUMI_CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   static const int cpl = [] { const char* e = getenv("LUMI_ROI_CPL"); return (e && atoi(e) == 4) ? 4 : 8; }();
   // (measured alternatives at R = 2000, batch 8: 4 channels/lane 3.1 ms, straight-line 16-tap loads
   //  without sharing 3.0 ms, this kernel 2.7 ms)

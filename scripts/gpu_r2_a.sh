@@ -11,6 +11,9 @@ timeout -s KILL 600 python bench.py --workload ssd --steps 20 --warmup 3 --layer
 echo "bench ssd exit $?" >> gpurun_out/a_summary.txt
 timeout -s KILL 600 python bench.py --workload frcnn_r101 --steps 10 --warmup 3 --layers --no-cpu-baseline > gpurun_out/a_bench_r101.json 2> gpurun_out/a_bench_r101.err
 echo "bench r101 exit $?" >> gpurun_out/a_summary.txt
+# ROI kernel A/B (category_ms_per_step.roi_pool): round-1 cell kernel vs the column-walk kernel at 4 / 8 channels per lane
+LUMI_ROI_KERNEL=cells timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/a_bench_r50_roi_cells.json 2>/dev/null
+LUMI_ROI_COLS_CPL=8 timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/a_bench_r50_roi_cols8.json 2>/dev/null
 for wl in ssd frcnn_r101; do
   timeout -s KILL 1200 ncu --set full --clock-control none --profile-from-start off -f -o /tmp/ncu_$wl python bench.py --workload $wl --ncu-range --ncu-unpiped --no-cpu-baseline > gpurun_out/a_ncu_$wl.log 2>&1
   echo "ncu $wl exit $?" >> gpurun_out/a_summary.txt
@@ -20,7 +23,7 @@ tail -n 15 gpurun_out/a_pytest_gpu.log
 cat gpurun_out/a_summary.txt
 python - <<'PY'
 import json
-for wl in ('r50','ssd','r101'):
+for wl in ('r50','r50_roi_cells','r50_roi_cols8','ssd','r101'):
     try:
         d=json.load(open('gpurun_out/a_bench_%s.json'%wl)); print(wl, d['value'], d['ms_per_step'], d['e2e']['value'], d['category_ms_per_step'], d['roofline']['frac'])
     except Exception as e: print(wl, 'ERR', e)
