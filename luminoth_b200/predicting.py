@@ -89,14 +89,15 @@ def format_predictions(objects, labels, probs, scale_factor, class_labels=None):
                   key=lambda x: x['prob'], reverse=True)
 
 
-def load_checkpoint_weights(engine, job_dir):
+def load_checkpoint_weights(engine, job_dir, prefix=None):
     """The ``Saver.restore`` of ``predicting.py:51-63`` without TensorFlow: reads the latest Saver-V2 bundle under
     ``job_dir`` and returns {tf variable name: array} for exactly the variables the engine's plan uses (optimizer
     slots, ``global_step`` and never-executed layers such as ResNet-50's block4 are ignored, like a Saver built from
     the inference graph would).  Raises ``ValueError`` when the directory holds no checkpoint, a variable is
     missing or a shape differs."""
     from . import tf_checkpoint as tfc
-    prefix = tfc.latest_checkpoint(job_dir)                # ValueError('Could not find checkpoint in ...')
+    if prefix is None:
+        prefix = tfc.latest_checkpoint(job_dir)            # ValueError('Could not find checkpoint in ...')
     reader = tfc.BundleReader(prefix)
     weights, missing = {}, []
     for name, shape in engine.weight_specs():
@@ -132,6 +133,8 @@ class PredictorNetwork(object):
         get_model_type(config.model.type)                 # ValueError on unknown model types
         self.config = config
         self.engine = Engine(config, device=device, max_batch=max_batch)
+        if callable(weights):                             # e.g. lumi eval: one specific checkpoint of the run
+            weights = weights(self.engine)
         if weights is None:
             if config.train.job_dir:
                 job_dir = config.train.job_dir
@@ -155,6 +158,13 @@ class PredictorNetwork(object):
         by the size the preprocessing gives them (``target_size``); each group runs through the engine in chunks of
         ``max_batch`` -- a directory of equally sized frames (``predict.py:69-97``, video frames ``:100-171``) is
         one batched call per chunk instead of one call per image."""
+        return [format_predictions(boxes, labels, probs, scale, self.class_labels)
+                for boxes, labels, probs, scale in self.predict_batch_raw(images)]
+
+    def predict_batch_raw(self, images):
+        """The network's fetches per image, before the Python post-step of ``predicting.py:114-148``:
+        [(objects (K,4) float32 in PREPROCESSED-image pixels, labels (K,) int32, probs (K,) float32, scale_factor)]
+        in the caller's order (``lumi eval`` compares these with the scaled ground truth, ``eval.py:330-347``)."""
         images = [np.asarray(im) for im in images]
         if not images:
             return []
@@ -177,8 +187,7 @@ class PredictorNetwork(object):
                 boxes, scores, labels, counts = self.engine.predict_raw(batch)
                 for j, i in enumerate(chunk):
                     k = int(counts[j])
-                    out[i] = format_predictions(boxes[j, :k], labels[j, :k], scores[j, :k], sizes[i][2],
-                                                self.class_labels)
+                    out[i] = (boxes[j, :k].copy(), labels[j, :k].copy(), scores[j, :k].copy(), sizes[i][2])
         return out
 
     def _resize_on_device(self, images, nh, nw):

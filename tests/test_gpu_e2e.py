@@ -443,3 +443,52 @@ def test_full_size_batch_properties():
     for x, y in zip(base, eng.predict_raw(imgs)):
         np.testing.assert_array_equal(x, y)                      # two-stream pipeline is bit-neutral
     eng.close()
+
+
+def test_lumi_eval_on_the_engine_matches_the_oracle_pipeline(tmp_path):
+    """SURVEY 8f-3 (`lumi eval`, eval.py:23-224,487-650) end to end: a TFRecord split of PNG images in two sizes, a
+    Saver-V2 checkpoint under <job_dir>/<run_name>, the engine's batched forward, COCO-style AP/AR -- compared with the
+    same metric code fed by the CPU oracle's detections for the same records.  Ground truth = the oracle's own top
+    detections (truncated to integers), so the metrics are far from zero and sensitive to every stage."""
+    import io
+    from PIL import Image
+    from luminoth_b200 import eval as E
+    from luminoth_b200 import tf_checkpoint as tfc
+    cfg = frcnn_cfg('resnet_v1_50')
+    wts = synth.make_weights(cfg, seed=7)
+    run = tmp_path / 'jobs' / 'run1'
+    run.mkdir(parents=True)
+    tfc.write_bundle(str(run / 'model.ckpt-500'), dict(wts))
+    tfc.write_checkpoint_state(str(run), 'model.ckpt-500')
+    data = tmp_path / 'data'
+    data.mkdir()
+    ecfg = E.prepare_eval_config(frcnn_cfg('resnet_v1_50'), 'val', 100)
+    images = [synth.make_images(1, 600, 640, seed=50 + i)[0] for i in range(3)] + \
+             [synth.make_images(1, 375, 500, seed=60 + i)[0] for i in range(2)]
+    payloads, oracle_out = [], {'bboxes': [], 'classes': [], 'scores': [], 'gt_bboxes': [], 'gt_classes': []}
+    for i, img in enumerate(images):
+        objs, labels, probs, scale = opredict.network_outputs(img, wts, ecfg)        # resized-image coordinates
+        top = np.argsort(-probs)[:6]
+        gt = [{'label': int(labels[j]), 'xmin': int(objs[j][0] / scale), 'ymin': int(objs[j][1] / scale),
+               'xmax': int(objs[j][2] / scale), 'ymax': int(objs[j][3] / scale)} for j in top]
+        buf = io.BytesIO()
+        Image.fromarray(img).save(buf, format='PNG')
+        payloads.append(E.make_sequence_example({'width': img.shape[1], 'height': img.shape[0], 'depth': 3,
+                                                 'filename': 'img%d.png' % i, 'image_raw': buf.getvalue(), 'gt_boxes': gt}))
+        gts = E.scaled_ground_truth(img.shape, np.array([[g['xmin'], g['ymin'], g['xmax'], g['ymax'], g['label']] for g in gt]), ecfg)
+        oracle_out['bboxes'].append(objs); oracle_out['classes'].append(labels); oracle_out['scores'].append(probs)
+        oracle_out['gt_bboxes'].append(gts[:, :4]); oracle_out['gt_classes'].append(gts[:, 4])
+    E.write_tfrecord(str(data / 'val.tfrecords'), payloads)
+    cfg2 = frcnn_cfg('resnet_v1_50', ['train.job_dir=' + str(tmp_path / 'jobs'), 'train.run_name=run1',
+                                      'dataset.dir=' + str(data)])
+    logs = []
+    res = E.evaluate(cfg2, 'val', watch=False, max_detections=100, max_batch=2, log=logs.append)
+    assert len(res) == 1 and res[0]['global_step'] == 500
+    m = res[0]['metrics']
+    ap, ar = E.calculate_metrics(oracle_out, 20)
+    want = E.summarize_metrics(ap, ar)
+    assert m['total_evaluated'] == 5
+    assert want['AP@0.50'] > 0.2, 'the comparison must not be vacuous'
+    for k in want:
+        assert abs(m[k] - want[k]) <= 2e-3, (k, m[k], want[k])
+    assert any('Average Precision (AP) @ [0.50]' in l for l in logs)
