@@ -16,6 +16,7 @@
 #ifndef LUMINOTH_B200_H
 #define LUMINOTH_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -176,6 +177,15 @@ int lumi_op_class_detections(const float* boxes_in, const float* deltas, const f
                              float im_h, float im_w, float var0, float var1, float min_prob, float nms_threshold,
                              int class_max, int total_max, int ssd_order,
                              float* objects, int32_t* labels, float* probs, int32_t* count, void* stream);
+
+/* ---- input path: JPEG decode on the GPU with nvJPEG (bound at run time; LUMI_ECUDA when the
+ * library is not installed).  Replaces PIL's Image.open(...).convert('RGB') of predict.py:69-79 for JPEG files.
+ * data/nbytes: the encoded file.  out: RGB interleaved uint8 [h,w,3] -- host pointer (out_on_device = 0) or device
+ * pointer (1) of `capacity` bytes; out = NULL only queries *height / *width.  Note: nvJPEG and libjpeg differ by
+ * +-1..2 grey levels on chroma edges, so detections on nvJPEG pixels are not bit-comparable with the reference's. */
+int lumi_decode_jpeg(const unsigned char* data, size_t nbytes, int device, unsigned char* out, size_t capacity,
+                     int out_on_device, int* height, int* width);
+const char* lumi_jpeg_last_error(void);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, 'libluminoth_b200.so')
 OBJ_DIR = os.path.join(HERE, 'build')
-SOURCES = ['conv.cu', 'elementwise.cu', 'roi.cu', 'postproc.cu', 'engine.cu', 'ops_api.cu']
+SOURCES = ['conv.cu', 'elementwise.cu', 'roi.cu', 'postproc.cu', 'engine.cu', 'ops_api.cu', 'jpeg.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', 
               '--expt-relaxed-constexpr', '-I', os.path.join(ROOT, 'include')]
@@ -69,7 +69,7 @@ def build_library(force=False, verbose=False):
     # processes that load the library without torch.
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), 'lib64')
     cmd = ([nvcc, '-shared', '-cudart', 'shared', '-o', LIB] + objs +
-           ['-gencode', 'arch=compute_100a,code=sm_100a', '-Xlinker', '-rpath', '-Xlinker', cuda_lib])
+           ['-gencode', 'arch=compute_100a,code=sm_100a', '-Xlinker', '-rpath', '-Xlinker', cuda_lib, '-ldl'])
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))

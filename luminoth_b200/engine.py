@@ -56,6 +56,9 @@ SIGNATURES = {
                                        _c_i64_p]),
     'lumi_last_error': (ctypes.c_char_p, [ctypes.c_void_p]),
     'lumi_destroy': (None, [ctypes.c_void_p]),
+    'lumi_decode_jpeg': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                        ctypes.c_int, _c_int_p, _c_int_p]),
+    'lumi_jpeg_last_error': (ctypes.c_char_p, []),
     'lumi_op_last_error': (ctypes.c_char_p, []),
     'lumi_op_conv2d': (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] + [ctypes.c_int] * 6 +
                        [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2 + [ctypes.c_void_p, _c_int_p, _c_int_p,
@@ -98,6 +101,23 @@ def load_library():
             fn.argtypes = args
         _lib = lib
         return lib
+
+
+def decode_jpeg(data, device=0):
+    """JPEG bytes -> (H, W, 3) uint8 RGB numpy array, decoded on the GPU by nvJPEG (``lumi_decode_jpeg``).
+    RuntimeError when nvJPEG / a CUDA device is unavailable or the stream is not a decodable JPEG."""
+    lib = load_library()
+    buf = (ctypes.c_ubyte * len(data)).from_buffer_copy(data)
+    h, w = ctypes.c_int(), ctypes.c_int()
+    rc = lib.lumi_decode_jpeg(buf, len(data), int(device), None, 0, 0, ctypes.byref(h), ctypes.byref(w))
+    if rc != LUMI_OK:
+        raise RuntimeError('lumi_decode_jpeg: ' + lib.lumi_jpeg_last_error().decode())
+    out = np.empty((h.value, w.value, 3), np.uint8)
+    rc = lib.lumi_decode_jpeg(buf, len(data), int(device), out.ctypes.data_as(ctypes.c_void_p), out.nbytes, 0,
+                              ctypes.byref(h), ctypes.byref(w))
+    if rc != LUMI_OK:
+        raise RuntimeError('lumi_decode_jpeg: ' + lib.lumi_jpeg_last_error().decode())
+    return out
 
 
 def _raise(code, msg):

@@ -492,3 +492,24 @@ def test_lumi_eval_on_the_engine_matches_the_oracle_pipeline(tmp_path):
     for k in want:
         assert abs(m[k] - want[k]) <= 2e-3, (k, m[k], want[k])
     assert any('Average Precision (AP) @ [0.50]' in l for l in logs)
+
+
+def test_nvjpeg_decode_close_to_pil():
+    """`lumi_decode_jpeg` (nvJPEG, GPU) vs PIL/libjpeg (the reference's decoder, predict.py:72-79) on a
+    4:2:0 and a 4:4:4 file: same shape, pixels within a few grey levels (the IDCT / chroma up-sampling differ)."""
+    import io
+    from PIL import Image
+    from luminoth_b200.engine import decode_jpeg
+    yy, xx = np.mgrid[0:96, 0:128]
+    img = np.stack([(yy * 2 + xx) % 256, (xx * 2) % 256, (yy + 2 * xx) % 256], -1).astype(np.uint8)
+    img = np.asarray(Image.fromarray(img).resize((256, 192), Image.BILINEAR))           # smooth content
+    for subsampling in (0, 2):
+        buf = io.BytesIO()
+        Image.fromarray(img).save(buf, format='JPEG', quality=92, subsampling=subsampling)
+        got = decode_jpeg(buf.getvalue())
+        ref = np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert('RGB'))
+        assert got.shape == ref.shape == (192, 256, 3) and got.dtype == np.uint8
+        d = np.abs(got.astype(int) - ref.astype(int))
+        assert d.mean() < 1.0 and np.percentile(d, 99.9) <= 6, (subsampling, d.mean(), d.max())
+    with pytest.raises(RuntimeError):
+        decode_jpeg(b'this is not a jpeg stream at all')
