@@ -112,6 +112,13 @@ int lumi_set_conv_streamk(lumi_engine* e, int mode);
  * identical either way (images are independent). Off automatically while profiling or tapping. */
 int lumi_set_pipeline(lumi_engine* e, int enable);
 
+/* 1 (default): the forward of every (half-)batch shape is captured into a CUDA graph the second time the shape is
+ * seen and replayed afterwards (one launch instead of ~40-75 kernels: removes the launch gaps that bound small-batch
+ * latency). 0: plain stream launches. Results are bit-identical either way. Env LUMI_GRAPHS=0 sets the default.
+ * lumi_last_graph_replays: how many (half-)batch forwards of the last lumi_predict were graph replays. */
+int lumi_set_graphs(lumi_engine* e, int enable);
+int lumi_last_graph_replays(lumi_engine* e);
+
 /* 1: also materialise intermediates the fused production path never writes (the "roi_pool" tap when
  * ROI crop + max-pool + mean run as one kernel) -- config.train.debug in the reference. Default 0. */
 int lumi_set_debug_taps(lumi_engine* e, int enable);

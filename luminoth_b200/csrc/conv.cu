@@ -515,6 +515,7 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
       if (item.k1 != n_iters) {
         // this CTA holds the head of the tile: the following CTAs hold the rest (they computed it first thing)
         const long long tile_end = (long long)(t + 1) * n_iters;
+        int last = blockIdx.x;
         for (int cta = blockIdx.x + 1;; ++cta) {
           int seen;
           do {
@@ -523,8 +524,15 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
           const float* wsp = a.sk_partials + (size_t)cta * (128 * BN) + (size_t)(half * HC) * 128 + row;
 #pragma unroll
           for (int j = 0; j < HC; ++j) racc[j] = __fadd_rn(racc[j], __ldcg(wsp + j * 128));
+          last = cta;
           if (TcSched::range_end(cta, total_tiles, n_iters) >= tile_end) break;
         }
+        // every flag is consumed by exactly one CTA (the one holding the tile's head): clear it once all eight
+        // epilogue warps are past their polls, so a REPLAY of this launch with the same epoch (CUDA graph) starts clean
+        named_bar_sync(3, 256);
+        if (warp == 2 && lane == 0)
+          for (int cta = blockIdx.x + 1; cta <= last; ++cta)
+            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(a.sk_flags + cta), "r"(0) : "memory");
       }
 
       // ---- scale/bias (folded BN) -> +residual -> activation -> store (overlaps the next tile's MMAs)

@@ -22,6 +22,7 @@
 #include <memory>
 #include <set>
 #include <string>
+#include <tuple>
 #include <vector>
 
 using namespace lumi;
@@ -120,6 +121,23 @@ struct lumi_engine {
   float* d_records = nullptr;   // caller-owned device buffer [max_batch][1 + 6*kmax] (lumi_set_record_output) or null
   std::map<std::string, Tap> taps;
   int planned_n = 0, planned_h = 0, planned_w = 0;
+  // CUDA graphs: one captured graph per (half-)batch forward, keyed by everything baked into its nodes
+  struct GraphKey {
+    int half, n, h, w, esz, img_off, conv_impl, streamk, reserve;
+    const void* records;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(half, n, h, w, esz, img_off, conv_impl, streamk, reserve, records) <
+             std::tie(o.half, o.n, o.h, o.w, o.esz, o.img_off, o.conv_impl, o.streamk, o.reserve, o.records);
+    }
+  };
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int launches = 0; int seen = 0; };
+  std::map<GraphKey, GraphEntry> graphs;
+  int use_graphs = 0;           // lumi_set_graphs / env LUMI_GRAPHS; off while profiling or tapping
+  int graph_replays = 0;        // forwards served by a graph replay in the last lumi_predict
+  void drop_graphs() {
+    for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs.clear();
+  }
   // per-category device timing (CUDA events on the engine stream), for bench.py's roofline
   bool profile = false;
   struct ProfSpan { int cat; cudaEvent_t a, b; double work; std::string label; };
@@ -128,6 +146,7 @@ struct lumi_engine {
   std::string prof_text, prof_layers_text;
 
   ~lumi_engine() {
+    drop_graphs();
     for (auto& kv : layers) conv_layer_free(kv.second);
     for (auto& kv : dev_vecs) cudaFree(kv.second);
     nms_workspace_free(ws_rpn); nms_workspace_free(ws_det);
@@ -659,6 +678,9 @@ void ensure_frcnn_anchors(lumi_engine* e, int h, int w, cudaStream_t st) {
   // fasterrcnn.py:261-308; the grid follows the block3 feature map: four ceil-halvings of the image size
   const int fh = cdiv(h, 16), fw = cdiv(w, 16);
   if (e->anchors_fh == fh && e->anchors_fw == fw) return;
+  e->drop_graphs();                            // graphs of other image sizes hold the old anchor buffer
+  LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  if (e->stream2) LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream2));
   const int na = fh * fw * e->A;
   cudaFree(e->d_anchors);
   e->d_anchors = nullptr;
@@ -962,6 +984,7 @@ Ctx make_ctx(lumi_engine* e, bool dry, int half) {
 
 void ensure_arena(lumi_engine* e, Arena& a, size_t need_bytes) {
   if (need_bytes <= a.cap) return;
+  e->drop_graphs();                            // captured nodes point into the old arena
   LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   if (e->stream2) LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream2));
   cudaFree(a.base);
@@ -978,6 +1001,7 @@ void ensure_image_capacity(lumi_engine* e, int h, int w) {
   const long na = (long)cdiv(h, 16) * cdiv(w, 16) * e->A;
   LUMI_REQUIRE(na < (1L << 30), "lumi_predict: image too large");
   if (na <= e->ws_rpn.cap) return;
+  e->drop_graphs();
   LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   if (e->stream2) LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream2));
   nms_workspace_free(e->ws_rpn);
@@ -1111,6 +1135,7 @@ int lumi_finalize(lumi_engine* e) {
   }
   conv_workspace_create(e->sk_ws[0]);
   if (const char* v = std::getenv("LUMI_CONV_STREAMK")) e->conv_streamk = std::max(0, std::min(2, std::atoi(v)));
+  if (const char* v = std::getenv("LUMI_GRAPHS")) e->use_graphs = std::atoi(v) != 0;
   if (e->max_batch >= 2) {
     conv_workspace_create(e->sk_ws[1]);
     LUMI_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
@@ -1122,6 +1147,44 @@ int lumi_finalize(lumi_engine* e) {
   e->finalized = true;
   return LUMI_OK;
   LUMI_API_END(e)
+}
+
+// One (half-)batch forward on cx.st: eager the first time a shape is seen (tensor maps, function attributes and the
+// arena plan settle), captured into a CUDA graph the second time, replayed from then on.  A replay is ONE launch
+// instead of ~40-75: the inter-kernel gaps (2-3 us each) and the CPU launch cost disappear, which is what bounds the
+// small-batch latency (`lumi predict` on single images, video frames).  Everything a node bakes in is part of the key.
+static void run_forward(lumi_engine* e, Ctx& cx, int half, const void* images, int n, int h, int w, int esz) {
+  const bool graphable = e->use_graphs && !e->profile && !e->debug_taps;
+  if (!graphable) { forward(cx, images, n, h, w); return; }
+  lumi_engine::GraphKey key{half, n, h, w, esz, cx.img_off, e->conv_impl, e->conv_streamk, cx.sm_reserve, e->d_records};
+  lumi_engine::GraphEntry& ent = e->graphs[key];
+  if (ent.exec) {
+    LUMI_CUDA_CHECK(cudaGraphLaunch(ent.exec, cx.st));
+    g_launch_count += ent.launches;
+    e->graph_replays++;
+    return;
+  }
+  if (ent.seen++ == 0) { forward(cx, images, n, h, w); return; }     // first sight: eager warm-up of this shape
+  const int before = g_launch_count;
+  cudaGraph_t graph = nullptr;
+  LUMI_CUDA_CHECK(cudaStreamBeginCapture(cx.st, cudaStreamCaptureModeThreadLocal));
+  try {
+    forward(cx, images, n, h, w);
+  } catch (...) {
+    cudaStreamEndCapture(cx.st, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    throw;
+  }
+  LUMI_CUDA_CHECK(cudaStreamEndCapture(cx.st, &graph));
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  LUMI_CUDA_CHECK(ce);
+  ent.exec = exec;
+  ent.launches = g_launch_count - before;
+  LUMI_CUDA_CHECK(cudaGraphLaunch(ent.exec, cx.st));
+  e->graph_replays++;
 }
 
 static int predict_impl(lumi_engine* e, const void* images, int esz, int images_on_device, int n, int h, int w,
@@ -1149,9 +1212,14 @@ static int predict_impl(lumi_engine* e, const void* images, int esz, int images_
   const uint8_t* dimg = static_cast<const uint8_t*>(images);
   const size_t img_bytes = (size_t)n * h * w * 3 * esz;
   const size_t bytes_a = (size_t)nA * h * w * 3 * esz;
-  if (!images_on_device) {
+  // graphs read their pixels from the engine's own staging buffer (a caller's device pointer changes per call)
+  const bool graphs_on = e->use_graphs && !e->profile && !e->debug_taps;
+  const bool stage = !images_on_device || graphs_on;
+  if (stage) {
     if (img_bytes > e->images_cap) {
+      e->drop_graphs();
       LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      if (e->stream2) LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream2));
       cudaFree(e->d_images);
       e->d_images = nullptr; e->images_cap = 0;
       LUMI_CUDA_CHECK(cudaMalloc(&e->d_images, img_bytes));
@@ -1159,7 +1227,9 @@ static int predict_impl(lumi_engine* e, const void* images, int esz, int images_
     }
     dimg = e->d_images;
   }
+  const cudaMemcpyKind up = images_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   g_launch_count = 0;
+  e->graph_replays = 0;
   if (e->type == "fasterrcnn") ensure_frcnn_anchors(e, h, w, e->stream);
   Ctx cx = make_ctx(e, false, 0);
   cx.img_f32 = esz == 4;
@@ -1172,19 +1242,18 @@ static int predict_impl(lumi_engine* e, const void* images, int esz, int images_
     cb.img_f32 = cx.img_f32;
     cb.sm_reserve = cx.sm_reserve;
     // each half uploads its own images on its own stream: the second half's H2D overlaps the first half's kernels
-    if (!images_on_device) {
-      LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_images, images, bytes_a, cudaMemcpyHostToDevice, e->stream));
+    if (stage) {
+      LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_images, images, bytes_a, up, e->stream));
       LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_images + bytes_a, static_cast<const uint8_t*>(images) + bytes_a,
-                                      img_bytes - bytes_a, cudaMemcpyHostToDevice, e->stream2));
+                                      img_bytes - bytes_a, up, e->stream2));
     }
-    forward(cx, dimg, nA, h, w);
-    forward(cb, dimg + bytes_a, nB, h, w);
+    run_forward(e, cx, 0, dimg, nA, h, w, esz);
+    run_forward(e, cb, 1, dimg + bytes_a, nB, h, w, esz);
     LUMI_CUDA_CHECK(cudaEventRecord(e->ev_join, e->stream2));
     LUMI_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
   } else {
-    if (!images_on_device)
-      LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_images, images, img_bytes, cudaMemcpyHostToDevice, e->stream));
-    forward(cx, dimg, n, h, w);
+    if (stage) LUMI_CUDA_CHECK(cudaMemcpyAsync(e->d_images, images, img_bytes, up, e->stream));
+    run_forward(e, cx, 0, dimg, n, h, w, esz);
   }
   e->launches = g_launch_count;
   const size_t k = (size_t)e->kmax;
@@ -1249,6 +1318,14 @@ int lumi_set_pipeline(lumi_engine* e, int enable) {
   e->pipeline = enable != 0;
   return LUMI_OK;
 }
+
+int lumi_set_graphs(lumi_engine* e, int enable) {
+  if (!e) return LUMI_EINVAL;
+  e->use_graphs = enable != 0;
+  return LUMI_OK;
+}
+
+int lumi_last_graph_replays(lumi_engine* e) { return e ? e->graph_replays : 0; }
 
 int lumi_set_debug_taps(lumi_engine* e, int enable) {
   if (!e) return LUMI_EINVAL;

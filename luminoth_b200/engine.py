@@ -49,6 +49,8 @@ SIGNATURES = {
     'lumi_set_conv_streamk': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'lumi_set_debug_taps': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'lumi_set_pipeline': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    'lumi_set_graphs': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    'lumi_last_graph_replays': (ctypes.c_int, [ctypes.c_void_p]),
     'lumi_profile_enable': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'lumi_profile_read': (ctypes.c_char_p, [ctypes.c_void_p]),
     'lumi_profile_read_layers': (ctypes.c_char_p, [ctypes.c_void_p]),
@@ -261,6 +263,14 @@ class Engine(object):
 
     def set_pipeline(self, enable=True):
         self._lib.lumi_set_pipeline(self._h, int(bool(enable)))
+
+    def set_graphs(self, enable=True):
+        """CUDA-graph replay of the forward (default on): bit-identical results, one launch per (half-)batch."""
+        self._lib.lumi_set_graphs(self._h, int(bool(enable)))
+
+    @property
+    def last_graph_replays(self):
+        return self._lib.lumi_last_graph_replays(self._h)
 
     def set_debug_taps(self, enable=True):
         self._lib.lumi_set_debug_taps(self._h, int(bool(enable)))

@@ -102,3 +102,48 @@ def test_record_output_equals_packed_outputs(with_rcnn):
     assert bool((rec == -7.0).all())
     del rec, boxes, scores, labels, counts, imgs
     eng.close()
+
+
+@pytest.mark.parametrize('model', ['fasterrcnn', 'ssd'])
+def test_cuda_graph_replay_is_bit_identical(model):
+    """lumi_set_graphs(1): the forward of a shape runs eagerly the first time, is captured the second time and
+    replayed afterwards.  Every call must give the eager result bit for bit -- both pipeline halves, the
+    stream-K schedule (its flags are cleared by the consumer, so a replay with the captured epoch starts clean),
+    after switching to another shape and back, and through the host (H2D staged) and device entry points."""
+    import torch
+    if model == 'fasterrcnn':
+        cfg = _cfg()
+        shapes = [(3, 224, 320), (1, 160, 224)]
+    else:
+        cfg = default_config('ssd', ['model.proposals.min_prob_threshold=0.2'])
+        shapes = [(3, 300, 300), (1, 300, 300)]
+    wts = synth.make_weights(cfg, seed=1)
+    eng = Engine(cfg, max_batch=3, max_h=shapes[0][1], max_w=shapes[0][2])
+    eng.load_weights(wts).finalize()
+    eng.set_conv_streamk('always')
+    batches = [synth.make_images(n, h, w, seed=10 + i) for i, (n, h, w) in enumerate(shapes)]
+    eng.set_graphs(False)
+    want = [eng.predict_raw(b) for b in batches]
+    eng.set_graphs(True)
+    for rnd in range(4):
+        for b, w_ in zip(batches, want):
+            got = eng.predict_raw(b)
+            for x, y in zip(got, w_):
+                np.testing.assert_array_equal(x, y)
+            if rnd >= 2:
+                assert eng.last_graph_replays >= 1, 'the forward must be served by a graph replay by now'
+    # device entry point: inputs are staged into the engine's buffer, so one graph serves any caller pointer
+    K = eng.max_detections
+    n = shapes[0][0]
+    outs = [torch.empty((n, K, 4), device='cuda'), torch.empty((n, K), device='cuda'),
+            torch.empty((n, K), dtype=torch.int32, device='cuda'), torch.empty((n,), dtype=torch.int32, device='cuda')]
+    for _ in range(2):
+        dimg = torch.from_numpy(batches[0]).cuda()
+        eng.predict_device(dimg, *outs)
+        eng.synchronize()
+        for x, y in zip(outs, want[0]):
+            np.testing.assert_array_equal(x.cpu().numpy(), y)
+    assert eng.last_graph_replays >= 1
+    assert int(want[0][3].sum()) > 0
+    del outs, dimg
+    eng.close()
