@@ -90,7 +90,8 @@ struct lumi_engine {
   int A = 0, anchor_stride = 16;
   std::vector<int> anchor_ref;                // A x 4 int32 (truncated, quirk Q1)
   int* d_anchor_ref = nullptr;
-  float* d_anchors = nullptr; int anchors_fh = 0, anchors_fw = 0;
+  float* d_anchors = nullptr; int anchors_fh = 0, anchors_fw = 0;   // current grid (owned by anchor_grids)
+  std::map<std::pair<int, int>, float*> anchor_grids;
   RpnParams rpn{};
   int rpn_channels = 512, rpn_kh = 3, rpn_kw = 3, rpn_act = ACT_RELU6;
   std::vector<int> fc_sizes; int fc_act = ACT_RELU6;
@@ -151,7 +152,8 @@ struct lumi_engine {
     for (auto& kv : dev_vecs) cudaFree(kv.second);
     nms_workspace_free(ws_rpn); nms_workspace_free(ws_det);
     conv_workspace_free(sk_ws[0]); conv_workspace_free(sk_ws[1]);
-    cudaFree(d_anchor_ref); cudaFree(d_anchors); cudaFree(d_final_keys); cudaFree(d_ssd_anchors);
+    cudaFree(d_anchor_ref); cudaFree(d_final_keys); cudaFree(d_ssd_anchors);
+    for (auto& kv : anchor_grids) cudaFree(kv.second);
     cudaFree(arena.base); cudaFree(arena2.base); cudaFree(d_final_keys2); cudaFree(d_overflow); cudaFree(d_images);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -675,17 +677,27 @@ Act bottleneck(Ctx& cx, const std::string& s, Act x, int depth) {
 
 // ---------------------------------------------------------------- Faster R-CNN forward
 void ensure_frcnn_anchors(lumi_engine* e, int h, int w, cudaStream_t st) {
-  // fasterrcnn.py:261-308; the grid follows the block3 feature map: four ceil-halvings of the image size
+  // fasterrcnn.py:261-308; the grid follows the block3 feature map: four ceil-halvings of the image size.
+  // One buffer per grid shape, kept for the engine's lifetime: captured graphs of other image sizes keep pointing
+  // at theirs (a server sees a handful of distinct sizes).
   const int fh = cdiv(h, 16), fw = cdiv(w, 16);
   if (e->anchors_fh == fh && e->anchors_fw == fw) return;
-  e->drop_graphs();                            // graphs of other image sizes hold the old anchor buffer
-  LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-  if (e->stream2) LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream2));
-  const int na = fh * fw * e->A;
-  cudaFree(e->d_anchors);
-  e->d_anchors = nullptr;
-  LUMI_CUDA_CHECK(cudaMalloc(&e->d_anchors, (size_t)na * 4 * sizeof(float)));
-  launch_frcnn_anchors(e->d_anchor_ref, e->A, fh, fw, e->anchor_stride, e->d_anchors, st);
+  auto it = e->anchor_grids.find({fh, fw});
+  if (it == e->anchor_grids.end()) {
+    if (e->anchor_grids.size() >= 64) {          // bound the cache: forget everything (and the graphs that used it)
+      e->drop_graphs();
+      LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      if (e->stream2) LUMI_CUDA_CHECK(cudaStreamSynchronize(e->stream2));
+      for (auto& kv : e->anchor_grids) cudaFree(kv.second);
+      e->anchor_grids.clear();
+    }
+    const int na = fh * fw * e->A;
+    float* buf = nullptr;
+    LUMI_CUDA_CHECK(cudaMalloc(&buf, (size_t)na * 4 * sizeof(float)));
+    launch_frcnn_anchors(e->d_anchor_ref, e->A, fh, fw, e->anchor_stride, buf, st);
+    it = e->anchor_grids.emplace(std::make_pair(fh, fw), buf).first;
+  }
+  e->d_anchors = it->second;
   e->anchors_fh = fh; e->anchors_fw = fw;
 }
 
