@@ -25,6 +25,12 @@ for wl in ssd frcnn_r101; do
   echo "ncu $wl exit $?" >> gpurun_out/a_summary.txt
   python scripts/ncu_step_summary.py /tmp/ncu_$wl.ncu-rep $wl gpurun_out/a_ncu_$wl > gpurun_out/a_ncu_${wl}_summary.txt 2>&1
 done
+# source-level profile of the first six tcgen05 conv launches of a step (stem, block1 shortcut / conv1 / conv2 / conv3+res / conv1):
+# the short-K, epilogue-bound layers -- read here with `ncu -i ... --page source --csv`
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_tc_kernel -c 6 -f -o gpurun_out/a_prof_conv_first6 python bench.py --ncu-range --ncu-unpiped --no-cpu-baseline > gpurun_out/a_ncu_conv6.log 2>&1
+echo "ncu conv6 exit $?" >> gpurun_out/a_summary.txt
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:roi_pool -c 1 -f -o gpurun_out/a_prof_roi python bench.py --ncu-range --ncu-unpiped --no-cpu-baseline > gpurun_out/a_ncu_roi.log 2>&1
+echo "ncu roi exit $?" >> gpurun_out/a_summary.txt
 tail -n 15 gpurun_out/a_pytest_gpu.log
 cat gpurun_out/a_summary.txt
 python - <<'PY'
