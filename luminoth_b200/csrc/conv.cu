@@ -211,6 +211,7 @@ struct TcArgs {
   int tiles_w, tiles_h, tiles_n;   // M tiles per row / column / image groups
   int n_tiles;                     // C_out tiles (cout_pad / BN)
   int stride;                      // TMA traversal stride of the activation map (1 or 2)
+  int reverse;                     // 1: walk the output tiles last-to-first (serpentine order across consecutive layers)
   int* overflow;
   // stream-K (sk_mode != 0): the K loops of all tiles form one unit sequence that is cut into gridDim.x equal
   // contiguous ranges; a CTA that starts in the middle of a tile writes its partial accumulators to
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
       TcSched sched(a.sk_mode, total_tiles, n_iters);
       TcItem item;
       while (sched.next(item)) {
-        const int t = item.tile;
+        const int t = a.reverse ? total_tiles - 1 - item.tile : item.tile;
         const int nt = t % a.n_tiles, mt = t / a.n_tiles;
         const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
         const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
       TcItem item;
       while (sched.next(item)) {
         if (item.k0 != 0) continue;                 // partial contribution: no epilogue here
-        const int t = item.tile;
+        const int t = a.reverse ? total_tiles - 1 - item.tile : item.tile;
         const int nt = t % a.n_tiles, mt = t / a.n_tiles;
         const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
         const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
     TcSched sched(a.sk_mode, total_tiles, n_iters);
     TcItem item;
     for (; sched.next(item); ++tile_iter) {
-      const int t = item.tile;
+      const int t = a.reverse ? total_tiles - 1 - item.tile : item.tile;    // coordinates only: the schedule is unchanged
       const int n_acc_chunks = (item.k1 - item.k0 + TC_CHUNK_STAGES - 1) / TC_CHUNK_STAGES;
       const int nt = t % a.n_tiles, mt = t / a.n_tiles;
       const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
       }
       if (item.k1 != n_iters) {
         // this CTA holds the head of the tile: the following CTAs hold the rest (they computed it first thing)
-        const long long tile_end = (long long)(t + 1) * n_iters;
+        const long long tile_end = (long long)(item.tile + 1) * n_iters;
         int last = blockIdx.x;
         for (int cta = blockIdx.x + 1;; ++cta) {
           int seen;
@@ -889,6 +890,7 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   a.tiles_w = cdiv(io.wo, tw); a.tiles_h = cdiv(io.ho, th); a.tiles_n = cdiv(io.in.n, nb);
   a.n_tiles = L.cout_pad / bn;
   a.stride = L.stride;
+  a.reverse = io.reverse;
   a.overflow = io.overflow_flag;
   const bool res_tma = io.res.hi != nullptr && bn == 128 && L.cout % 128 == 0 && !io.out_f32;
   if (res_tma) {          // residual tile prefetched by TMA (box over the unit's input, subsampled by res_stride)

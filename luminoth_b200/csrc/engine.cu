@@ -116,6 +116,7 @@ struct lumi_engine {
   int* d_overflow = nullptr;
   ConvWorkspace sk_ws[2];       // stream-K scratch, one per stream
   int conv_streamk = 1;         // 0 off, 1 auto, 2 whenever possible
+  int conv_serpentine = 0;      // env LUMI_CONV_SERPENTINE: consecutive conv layers walk their tiles in opposite directions
   uint8_t* d_images = nullptr; size_t images_cap = 0;
   float* d_boxes = nullptr; float* d_scores = nullptr; int* d_labels = nullptr; int* d_counts = nullptr;
   int* d_prop_counts = nullptr;
@@ -563,6 +564,7 @@ struct Ctx {
   bool taps = true;             // record debug taps (first half only)
   bool img_f32 = false;         // input pixels are float32 (resized images) instead of uint8
   int sm_reserve = 0;           // SMs the persistent conv launches of this forward leave to the other stream
+  int conv_parity = 0;          // alternates per conv launch when the serpentine tile order is on
   Act act(int n, int h, int w, int c) {
     Act a; a.n = n; a.h = h; a.w = w; a.c = c;
     const size_t bytes = a.numel() * sizeof(__half);
@@ -642,6 +644,7 @@ Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* re
   io.sk = cx.sk;
   io.streamk = cx.e->conv_streamk;
   io.sm_reserve = cx.sm_reserve;
+  if (cx.e->conv_serpentine) { io.reverse = cx.conv_parity; cx.conv_parity ^= 1; }
   if (!cx.dry) {
     const bool tc = cx.e->conv_impl == 1 && conv_tc_supported(L, io);
     const double flops = algorithmic_flops >= 0 ? algorithmic_flops
@@ -1148,6 +1151,7 @@ int lumi_finalize(lumi_engine* e) {
   conv_workspace_create(e->sk_ws[0]);
   if (const char* v = std::getenv("LUMI_CONV_STREAMK")) e->conv_streamk = std::max(0, std::min(2, std::atoi(v)));
   if (const char* v = std::getenv("LUMI_GRAPHS")) e->use_graphs = std::atoi(v) != 0;
+  if (const char* v = std::getenv("LUMI_CONV_SERPENTINE")) e->conv_serpentine = std::atoi(v) != 0;
   if (e->max_batch >= 2) {
     conv_workspace_create(e->sk_ws[1]);
     LUMI_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));

@@ -14,6 +14,7 @@ echo "bench r101 exit $?" >> gpurun_out/a_summary.txt
 # ROI kernel A/B (category_ms_per_step.roi_pool): round-1 cell kernel vs the column-walk kernel at 4 / 8 channels per lane
 LUMI_ROI_KERNEL=cells timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/a_bench_r50_roi_cells.json 2>/dev/null
 LUMI_ROI_COLS_CPL=8 timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/a_bench_r50_roi_cols8.json 2>/dev/null
+LUMI_CONV_SERPENTINE=1 timeout -s KILL 300 python bench.py --steps 20 --warmup 4 --layers --no-cpu-baseline > gpurun_out/a_bench_r50_serp.json 2>/dev/null
 # CUDA graphs A/B (default off until validated): batch 8 and batch-1 / batch-2 latency
 LUMI_GRAPHS=1 timeout -s KILL 300 python bench.py --steps 20 --warmup 4 --no-cpu-baseline > gpurun_out/a_bench_r50_graphs.json 2> gpurun_out/a_bench_r50_graphs.err
 for b in 1 2; do
@@ -35,7 +36,7 @@ tail -n 15 gpurun_out/a_pytest_gpu.log
 cat gpurun_out/a_summary.txt
 python - <<'PY'
 import json
-for wl in ('r50','r50_roi_cells','r50_roi_cols8','r50_graphs','r50_b1','r50_b1_graphs','r50_b2','r50_b2_graphs','ssd','r101'):
+for wl in ('r50','r50_roi_cells','r50_roi_cols8','r50_serp','r50_graphs','r50_b1','r50_b1_graphs','r50_b2','r50_b2_graphs','ssd','r101'):
     try:
         d=json.load(open('gpurun_out/a_bench_%s.json'%wl)); print(wl, d['value'], d['ms_per_step'], d['e2e']['value'], d['category_ms_per_step'], d['roofline']['frac'])
     except Exception as e: print(wl, 'ERR', e)
