@@ -264,29 +264,39 @@ constexpr int TC_A_BYTES = 128 * 128;       // 128 pixel rows x 64 fp16 (one 128
 // K loop (their truncation error is 2^-11 times smaller still).
 constexpr int TC_CHUNK_STAGES = 4;          // 16 hi*hi MMAs per D1 chunk
 
-template <int BN, int STAGES, bool RES = false>
+// NSPLIT: column parts of the epilogue (4 warps = 4 TMEM lane quadrants per part): 2 -> 8 epilogue warps (long-K layers),
+// 4 -> 16 epilogue warps for the short-K layers whose tile time IS the epilogue (1x1 convs of block1/2/3: one to eight
+// K stages per tile against ~3.5 us of drain + BN + residual + split + store on 8 warps).
+// INPLACE (RES kernels with one 32-channel slab per part): the residual tile is TMA-loaded INTO the part's output
+// staging slab, updated in place and stored from there, so residual + staging cost 64 KB instead of 128 KB.
+template <int BN, int STAGES, bool RES = false, int NSPLIT = 2, bool INPLACE = false>
 struct TcCfg {
+  static_assert((BN / NSPLIT) % 32 == 0, "each epilogue part owns whole 32-channel slabs");
+  static_assert(!INPLACE || (RES && BN / NSPLIT == 32), "in-place residual needs exactly one slab per part");
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-  static constexpr int OUT_STAGE_BYTES = 2 * 2 * 128 * 64;   // per column half: hi + lo slabs of 128 rows x 32 ch
+  static constexpr int OUT_STAGE_BYTES = NSPLIT * 2 * 128 * 64;   // per column part: hi + lo slabs of 128 rows x 32 ch
   // RES: the whole residual tile (BN/32 slabs x {hi, lo} x 128 rows x 64 B) is TMA-prefetched at tile start
-  static constexpr int RES_STAGE_BYTES = RES ? (BN / 32) * 2 * 128 * 64 : 0;
+  static constexpr int RES_STAGE_BYTES = (RES && !INPLACE) ? (BN / 32) * 2 * 128 * 64 : 0;
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + OUT_STAGE_BYTES + RES_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 4 * BN;          // D1[0], D1[1], D2[0], D2[1]  (256 or 512 columns)
+  static constexpr int EPI_WARPS = 4 * NSPLIT;
+  static constexpr int RES_WARP = 2 + EPI_WARPS;    // residual-tile TMA producer (RES kernels)
+  static constexpr int THREADS = (2 + EPI_WARPS + (RES ? 1 : 0)) * 32;   // warp 0 TMA, warp 1 MMA, then the epilogue warps
 };
 
-constexpr int TC_THREADS = 320;                     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int TC_THREADS_RES = 352;                 // + warp 10: residual-tile TMA producer (RES kernels)
 
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, += gridDim.x.  The
 // TMA producer, the MMA issuer and the epilogue warps each iterate the same tile sequence with
 // free-running stage / chunk counters, so the producer prefetches the next tile's operands and the
 // tensor core starts the next tile while the epilogue warps are still storing the previous one
 // (D1 and D2 are double-buffered in TMEM).
-template <int BN, int STAGES, bool RES>
-__global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
-  using Cfg = TcCfg<BN, STAGES, RES>;
+template <int BN, int STAGES, bool RES, int NSPLIT, bool INPLACE>
+__global__ void __launch_bounds__(TcCfg<BN, STAGES, RES, NSPLIT, INPLACE>::THREADS, 1)
+conv_tc_kernel(const __grid_constant__ TcArgs a) {
+  using Cfg = TcCfg<BN, STAGES, RES, NSPLIT, INPLACE>;
+  constexpr int EPI_WARPS = Cfg::EPI_WARPS;
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment by OFFSET (not by integer round-trip) so the compiler keeps the shared address space
   // and emits LDS/STS for the staging buffers instead of generic LD/ST
@@ -310,9 +320,10 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&acc_full_bar[s], 1); mbar_init(&acc_empty_bar[s], 8); mbar_init(&d2_empty_bar[s], 8);
+      mbar_init(&acc_full_bar[s], 1); mbar_init(&acc_empty_bar[s], EPI_WARPS); mbar_init(&d2_empty_bar[s], EPI_WARPS);
     }
-    for (int s = 0; s < 4; ++s) { mbar_init(&res_full_bar[s], 1); mbar_init(&res_empty_bar[s], 4); }
+    // res_empty: the slab's four epilogue warps (separate residual staging) or the part's store leader (in place)
+    for (int s = 0; s < 4; ++s) { mbar_init(&res_full_bar[s], 1); mbar_init(&res_empty_bar[s], INPLACE ? 1 : 4); }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -402,8 +413,8 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
         }
       }
     }
-  } else if (warp == 10) {
-    if (RES && lane == 0) {
+  } else if (RES && warp == Cfg::RES_WARP) {
+    if (lane == 0) {
       // ---------------- residual producer: the shortcut tile of each output tile, one 32-channel slab (hi + lo
       // plane) per barrier pair, refilled as soon as its four epilogue warps have read the previous tile's slab.
       // It runs on its own warp so that it never holds back the operand loads of the next tile.
@@ -417,25 +428,27 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
         const int nt = t % a.n_tiles, mt = t / a.n_tiles;
         const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
         const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
+        // in place: slab sl lands in part sl's output staging (same {hi, lo} x 8 KB layout, same 64 B swizzle)
+        uint8_t* res_base = INPLACE ? out_stage : res_stage;
 #pragma unroll
         for (int i = 0; i < BN / 32; ++i) {
-          // consumption order: both column halves work on their first slab, then on their second
-          const int sl = (i % 2) * (BN / 64) + (i / 2);
+          // consumption order: every column part works on its first slab, then on its second, ...
+          const int sl = (i % NSPLIT) * (BN / 32 / NSPLIT) + (i / NSPLIT);
           mbar_wait(&res_empty_bar[sl], (tile_iter & 1u) ^ 1u);
           mbar_arrive_expect_tx(&res_full_bar[sl], slab_tx);
-          tma_load_4d(res_stage + (sl * 2 + 0) * 8192, &a.tm_r_hi, &res_full_bar[sl], n0 + sl * 32,
+          tma_load_4d(res_base + (sl * 2 + 0) * 8192, &a.tm_r_hi, &res_full_bar[sl], n0 + sl * 32,
                       x0 * a.res_stride, y0 * a.res_stride, img0);
-          tma_load_4d(res_stage + (sl * 2 + 1) * 8192, &a.tm_r_lo, &res_full_bar[sl], n0 + sl * 32,
+          tma_load_4d(res_base + (sl * 2 + 1) * 8192, &a.tm_r_lo, &res_full_bar[sl], n0 + sl * 32,
                       x0 * a.res_stride, y0 * a.res_stride, img0);
         }
         ++tile_iter;
       }
     }
   } else {
-    // ---------------- epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp-2)/4
-    constexpr int HC = BN / 2;                          // columns owned by this warp
+    // ---------------- epilogue warps 2..: TMEM lane quadrant = warp % 4, column part = (warp-2)/4
+    constexpr int HC = BN / NSPLIT;                     // columns owned by this warp
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;                   // column part 0..NSPLIT-1 (named `half` since the 2-part kernel)
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t gchunk = 0, tile_iter = 0, epi_iter = 0;
@@ -508,7 +521,7 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
 #pragma unroll
         for (int j = 0; j < HC; ++j) wsp[j * 128] = racc[j];
         __threadfence();
-        named_bar_sync(3, 256);                          // all 8 epilogue warps have written and fenced
+        named_bar_sync(7, 32 * EPI_WARPS);               // all epilogue warps have written and fenced
         if (warp == 2 && lane == 0)
           asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.sk_flags + blockIdx.x), "r"(a.sk_epoch) : "memory");
         continue;
@@ -528,9 +541,9 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
           last = cta;
           if (TcSched::range_end(cta, total_tiles, n_iters) >= tile_end) break;
         }
-        // every flag is consumed by exactly one CTA (the one holding the tile's head): clear it once all eight
+        // every flag is consumed by exactly one CTA (the one holding the tile's head): clear it once all
         // epilogue warps are past their polls, so a REPLAY of this launch with the same epoch (CUDA graph) starts clean
-        named_bar_sync(3, 256);
+        named_bar_sync(7, 32 * EPI_WARPS);
         if (warp == 2 && lane == 0)
           for (int cta = blockIdx.x + 1; cta <= last; ++cta)
             asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(a.sk_flags + cta), "r"(0) : "memory");
@@ -540,7 +553,7 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
       // split outputs: each column half (4 warps) stages a 128 x 32-channel slab per plane in shared
       // memory (64 B swizzle) and one thread issues the two bulk tensor stores -- fully coalesced, and
       // TMA clips partial tiles; fp32 outputs (head layers) are written directly.
-      uint8_t* st_hi = out_stage + half * (Cfg::OUT_STAGE_BYTES / 2);
+      uint8_t* st_hi = out_stage + half * (2 * 128 * 64);
       uint8_t* st_lo = st_hi + 128 * 64;
       const bool store_leader = ((warp - 2) & 3) == 0 && lane == 0;     // one issuing thread per column half
 #pragma unroll
@@ -563,8 +576,9 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
             const int sl = half * (HC / 32) + ch;
             mbar_wait(&res_full_bar[sl], epi_iter & 1u);
             const int rsw = (row >> 1) & 3;
-            const uint8_t* rh = res_stage + (sl * 2 + 0) * 8192 + row * 64;
-            const uint8_t* rl = res_stage + (sl * 2 + 1) * 8192 + row * 64;
+            const uint8_t* rbase = INPLACE ? out_stage : res_stage;     // in place: this part's own staging slab
+            const uint8_t* rh = rbase + (sl * 2 + 0) * 8192 + row * 64;
+            const uint8_t* rl = rbase + (sl * 2 + 1) * 8192 + row * 64;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const uint4 h4 = *reinterpret_cast<const uint4*>(rh + ((g ^ rsw) << 4));
@@ -574,8 +588,10 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[g * 8 + j] += join_f16(ph[j], pl[j]);
             }
-            __syncwarp();              // this warp is done with the slab
-            if (lane == 0) mbar_arrive(&res_empty_bar[sl]);
+            if (!INPLACE) {            // (in place the slab is released by the store leader once the store has read it)
+              __syncwarp();            // this warp is done with the slab
+              if (lane == 0) mbar_arrive(&res_empty_bar[sl]);
+            }
           } else if (a.res_hi && valid) {     // residual tensors always have cout % 32 == 0 channels
             const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + rpix * a.cout + c0);
             const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + rpix * a.cout + c0);
@@ -618,8 +634,10 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
             const uint32_t ab = *reinterpret_cast<const uint32_t*>(&amax);
             const bool ovf = ((ab & 0x7C00u) == 0x7C00u) || ((ab & 0x7C000000u) == 0x7C000000u);
             if (ovf && valid && a.overflow) atomicOr(a.overflow, 1);
-            if (store_leader) bulk_wait_group_read0();   // the previous slab's stores have drained the staging
-            named_bar_sync(1 + half, 128);
+            if (!INPLACE) {            // (in place: res_full already implies that the previous store has read the slab)
+              if (store_leader) bulk_wait_group_read0();   // the previous slab's stores have drained the staging
+              named_bar_sync(1 + half, 128);
+            }
             const int sw = (row >> 1) & 3;               // SWIZZLE_64B: 16 B chunk index ^= address bits [7:8]
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -632,6 +650,10 @@ __global__ void __launch_bounds__(RES ? TC_THREADS_RES : TC_THREADS, 1) conv_tc_
               tma_store_4d(&a.tm_o_hi, st_hi, c0, x0, y0, img0);
               tma_store_4d(&a.tm_o_lo, st_lo, c0, x0, y0, img0);
               bulk_commit_group();
+              if (INPLACE) {           // hand the slab back to the residual producer once the store has read it
+                bulk_wait_group_read0();
+                mbar_arrive(&res_empty_bar[half]);
+              }
             }
           }
         }
@@ -821,16 +843,16 @@ void conv_workspace_free(ConvWorkspace& w) {
   w.partials = nullptr; w.flags = nullptr; w.ctas = 0;
 }
 
-template <int BN, int STAGES, bool RES>
+template <int BN, int STAGES, bool RES, int NSPLIT = 2, bool INPLACE = false>
 static void launch_tc_cfg(const TcArgs& a, ConvWorkspace* sk, int streamk, int sm_reserve, cudaStream_t st) {
-  using Cfg = TcCfg<BN, STAGES, RES>;
+  using Cfg = TcCfg<BN, STAGES, RES, NSPLIT, INPLACE>;
   // cudaFuncSetAttribute is per device: one flag per (kernel instance, device)
   static bool attr_set[LUMI_MAX_DEVICES] = {false};
   int dev = 0;
   LUMI_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= LUMI_MAX_DEVICES || !__atomic_load_n(&attr_set[dev], __ATOMIC_ACQUIRE)) {
-    LUMI_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES));
+    LUMI_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (dev >= 0 && dev < LUMI_MAX_DEVICES) __atomic_store_n(&attr_set[dev], true, __ATOMIC_RELEASE);
   }
   const long total = (long)a.tiles_w * a.tiles_h * a.tiles_n * a.n_tiles;
@@ -856,7 +878,7 @@ static void launch_tc_cfg(const TcArgs& a, ConvWorkspace* sk, int streamk, int s
       grid = sms;
     }
   }
-  conv_tc_kernel<BN, STAGES, RES><<<grid, RES ? TC_THREADS_RES : TC_THREADS, Cfg::SMEM_BYTES, st>>>(args);
+  conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(args);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
@@ -893,12 +915,16 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   a.reverse = io.reverse;
   a.overflow = io.overflow_flag;
   const bool res_tma = io.res.hi != nullptr && bn == 128 && L.cout % 128 == 0 && !io.out_f32;
+  // 16 epilogue warps for the short-K layers (<= 8 K stages per tile: their tile time is the epilogue)
+  const bool epi16 = io.epi16 && bn == 128 && !io.out_f32 && (long)L.kh * L.kw * (L.cin >> 6) <= 8;
   if (res_tma) {          // residual tile prefetched by TMA (box over the unit's input, subsampled by res_stride)
     a.tm_r_hi = cached_out_map(io.res.hi, io.res.n, io.res.h, io.res.w, io.res.c, nb, th, tw, io.res_stride);
     a.tm_r_lo = cached_out_map(io.res.lo, io.res.n, io.res.h, io.res.w, io.res.c, nb, th, tw, io.res_stride);
-    launch_tc_cfg<128, 2, true>(a, io.sk, io.streamk, io.sm_reserve, st);
+    if (epi16) launch_tc_cfg<128, 2, true, 4, true>(a, io.sk, io.streamk, io.sm_reserve, st);
+    else launch_tc_cfg<128, 2, true>(a, io.sk, io.streamk, io.sm_reserve, st);
   } else if (bn == 128) {
-    launch_tc_cfg<128, 3, false>(a, io.sk, io.streamk, io.sm_reserve, st);
+    if (epi16 && !io.res.hi) launch_tc_cfg<128, 2, false, 4, false>(a, io.sk, io.streamk, io.sm_reserve, st);
+    else launch_tc_cfg<128, 3, false>(a, io.sk, io.streamk, io.sm_reserve, st);
   } else {
     launch_tc_cfg<64, 4, false>(a, io.sk, io.streamk, io.sm_reserve, st);
   }

@@ -81,16 +81,28 @@ int lumi_op_conv2d(const float* x, int n, int h, int w, int cin, const float* wg
     launch_f32_to_act(residual, res->a, st);
     io.res = res->a; io.res_stride = 1;
   }
-  if (impl == 1 || impl == 2) {
+  if (impl >= 1 && impl <= 5) {
+    // 1 whole tiles, 2 stream-K forced (fp32 outputs written by the epilogue);
+    // 3 / 4 / 5: the engine's inter-layer form -- fp16x2 split planes through the staged TMA-store epilogue (and the
+    // TMA-prefetched residual) -- with the 8-warp epilogue (3), the 16-warp short-K kernels allowed (4), and 4 + stream-K (5)
+    std::unique_ptr<ActBuf> split_out;
+    if (impl >= 3) {
+      LUMI_REQUIRE(cout % 32 == 0, "conv2d: split outputs need cout % 32 == 0");
+      split_out.reset(new ActBuf(n, ho, wo, cout));
+      io.out = split_out->a;
+      io.out_f32 = nullptr;
+      io.epi16 = impl >= 4;
+    }
     LUMI_REQUIRE(conv_tc_supported(L, io), "conv2d: this layer shape is not handled by the tensor-core kernel");
     ConvWorkspace sk;
     struct SkGuard { ConvWorkspace& w; ~SkGuard() { conv_workspace_free(w); } } skg{sk};
-    if (impl == 2) {
+    if (impl == 2 || impl == 5) {
       conv_workspace_create(sk);
       io.sk = &sk;
       io.streamk = 2;
     }
     launch_conv_tc(L, io, st);
+    if (split_out) launch_act_to_f32(split_out->a, y, st);
     LUMI_CUDA_CHECK(cudaStreamSynchronize(st));
   } else {
     launch_conv_simt(L, io, st);

@@ -3,7 +3,7 @@
 # bench lines for the three workloads, one-step ncu --set full for SSD and R101 (r1 only had R50).
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/a_smi.txt 2>&1
-timeout -s KILL 1500 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/a_pytest_gpu.log 2>&1
+timeout -s KILL 1500 python -m pytest tests -m gpu -q -p no:cacheprovider -k "not epi16" --timeout 400 --timeout-method=thread > gpurun_out/a_pytest_gpu.log 2>&1
 echo "pytest gpu exit $?" > gpurun_out/a_summary.txt
 timeout -s KILL 600 python bench.py --steps 20 --warmup 3 --layers --no-cpu-baseline > gpurun_out/a_bench_r50.json 2> gpurun_out/a_bench_r50.err
 echo "bench r50 exit $? (must be 0: normal interpreter exit, no os._exit)" >> gpurun_out/a_summary.txt
@@ -32,11 +32,17 @@ timeout -s KILL 900 ncu --set full --clock-control none --import-source on --pro
 echo "ncu conv6 exit $?" >> gpurun_out/a_summary.txt
 timeout -s KILL 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:roi_pool -c 1 -f -o gpurun_out/a_prof_roi python bench.py --ncu-range --ncu-unpiped --no-cpu-baseline > gpurun_out/a_ncu_roi.log 2>&1
 echo "ncu roi exit $?" >> gpurun_out/a_summary.txt
+# LAST (new, untested kernels: a hang must not cost the rest of the call): 16-epilogue-warp conv kernels
+timeout -s KILL 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider -k "epi16" --timeout 120 --timeout-method=thread > gpurun_out/a_pytest_epi16.log 2>&1
+echo "pytest epi16 exit $?" >> gpurun_out/a_summary.txt
+LUMI_CONV_EPI16=1 timeout -s KILL 300 python bench.py --steps 20 --warmup 4 --layers --no-cpu-baseline > gpurun_out/a_bench_r50_epi16.json 2> gpurun_out/a_bench_r50_epi16.err
+echo "bench epi16 exit $?" >> gpurun_out/a_summary.txt
 tail -n 15 gpurun_out/a_pytest_gpu.log
+tail -n 8 gpurun_out/a_pytest_epi16.log
 cat gpurun_out/a_summary.txt
 python - <<'PY'
 import json
-for wl in ('r50','r50_roi_cells','r50_roi_cols8','r50_serp','r50_graphs','r50_b1','r50_b1_graphs','r50_b2','r50_b2_graphs','ssd','r101'):
+for wl in ('r50','r50_roi_cells','r50_roi_cols8','r50_serp','r50_epi16','r50_graphs','r50_b1','r50_b1_graphs','r50_b2','r50_b2_graphs','ssd','r101'):
     try:
         d=json.load(open('gpurun_out/a_bench_%s.json'%wl)); print(wl, d['value'], d['ms_per_step'], d['e2e']['value'], d['category_ms_per_step'], d['roofline']['frac'])
     except Exception as e: print(wl, 'ERR', e)

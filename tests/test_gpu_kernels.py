@@ -68,15 +68,22 @@ CONV_CASES = [
     # enough tiles that a stream-K range holds whole tiles plus a head and a tail piece
     ('sk_many_tiles', 2, 64, 96, 128, 256, 3, 1, 1, 'SAME', True, 1),
     ('sk_1x1_512_128', 3, 40, 64, 512, 128, 1, 1, 1, 'SAME', False, 1),
+    # short-K 1x1 layers of the bottlenecks (the 16-epilogue-warp kernels): residual in place / no residual / subsampled
+    ('b1_conv3_64_256_res', 2, 38, 64, 64, 256, 1, 1, 1, 'SAME', True, 1),
+    ('b1_shortcut_64_256', 2, 38, 64, 64, 256, 1, 1, 1, 'SAME', False, 0),
+    ('b2_conv3_128_512_res', 3, 19, 32, 128, 512, 1, 1, 1, 'SAME', True, 1),
+    ('b3_shortcut_512_1024', 1, 38, 64, 512, 1024, 1, 1, 1, 'SAME', False, 0),
 ]
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc_streamk'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc_streamk', 'tc_split', 'tc_split_epi16', 'tc_split_epi16_streamk'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv2d_matches_oracle(case, impl):
     name, n, h, w, cin, cout, k, stride, rate, padding, use_res, act = case
     if impl != 'simt' and cin % 64 != 0:
         pytest.skip('layer shape runs on the SIMT kernel by design')
+    if impl.startswith('tc_split') and cout % 32 != 0:
+        pytest.skip('split-plane outputs exist for cout % 32 == 0 (head layers write fp32)')
     import zlib
     rng = np.random.default_rng(zlib.crc32(name.encode()))
     x = (rng.standard_normal((n, h, w, cin)) * 2).astype(np.float32)
