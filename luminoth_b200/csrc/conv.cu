@@ -211,6 +211,7 @@ struct TcArgs {
   int tiles_w, tiles_h, tiles_n;   // M tiles per row / column / image groups
   int n_tiles;                     // C_out tiles (cout_pad / BN)
   int stride;                      // TMA traversal stride of the activation map (1 or 2)
+  int chunk_head, chunk_tail;      // D1 chunk schedule, see tc_chunk_end()
   int reverse;                     // 1: walk the output tiles last-to-first (serpentine order across consecutive layers)
   int* overflow;
   // stream-K (sk_mode != 0): the K loops of all tiles form one unit sequence that is cut into gridDim.x equal
@@ -262,7 +263,18 @@ constexpr int TC_A_BYTES = 128 * 128;       // 128 pixel rows x 64 fp16 (one 128
 // registers (round-to-nearest adds on the CUDA cores) every TC_CHUNK_STAGES pipeline stages; the
 // 2^-11-times-smaller cross terms hi*lo + lo*hi accumulate in their own TMEM tile D2 for the whole
 // K loop (their truncation error is 2^-11 times smaller still).
-constexpr int TC_CHUNK_STAGES = 4;          // 16 hi*hi MMAs per D1 chunk
+constexpr int TC_CHUNK_STAGES = 4;          // 16 hi*hi MMAs per D1 chunk (the first `chunk_head` stages of a work item)
+// D1 chunk schedule of a work item (deterministic: a function of the stage index only, shared by the MMA issuer and
+// the epilogue warps).  The first chunk_head stages run in TC_CHUNK_STAGES-stage chunks -- the previous tile's
+// epilogue is still occupying the drain warps then, and two 4-stage chunks are what the two D1 buffers can absorb --
+// the remaining stages in chunk_tail-stage chunks.  Truncation error grows with the MMAs per chunk (CPU model of the
+// truncating accumulator): 16 MMAs ~5e-7 relative per layer, 8 ~2.8e-7, 4 ~1.8e-7; fp32 FMA chains of a CPU
+// conv sit at ~2e-7.
+__device__ __forceinline__ int tc_chunk_end(int rel, int n_rel, int head, int tail) {
+  const int len = rel < head ? TC_CHUNK_STAGES : tail;
+  const int e = rel + len;
+  return e < n_rel ? e : n_rel;
+}
 
 // NSPLIT: column parts of the epilogue (4 warps = 4 TMEM lane quadrants per part): 2 -> 8 epilogue warps (long-K layers),
 // 4 -> 16 epilogue warps for the short-K layers whose tile time IS the epilogue (1x1 convs of block1/2/3: one to eight
@@ -382,14 +394,19 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
         tc_fence_after();
         const uint32_t d2 = tmem_base + (2u + tbuf) * BN;
         uint32_t d1 = 0, buf = 0;
+        const int n_rel = item.k1 - item.k0;
+        int chunk_begin = 0, chunk_stop = 0;           // current chunk = stages [chunk_begin, chunk_stop) of this item
         for (int it = item.k0; it < item.k1; ++it, ++git) {
-          const int in_chunk = (it - item.k0) % TC_CHUNK_STAGES;
-          if (in_chunk == 0) {
+          const int rel = it - item.k0;
+          if (rel == chunk_stop) {
+            chunk_begin = rel;
+            chunk_stop = tc_chunk_end(rel, n_rel, a.chunk_head, a.chunk_tail);
             buf = gchunk & 1u;
             mbar_wait(&acc_empty_bar[buf], ((gchunk >> 1) & 1u) ^ 1u);    // D1[buf] drained
             tc_fence_after();
             d1 = tmem_base + buf * BN;
           }
+          const bool first_of_chunk = rel == chunk_begin;
           const uint32_t st = git % STAGES, ph = (git / STAGES) & 1u;
           mbar_wait(&full_bar[st], ph);
           tc_fence_after();
@@ -401,12 +418,12 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ko = (uint64_t)(k * 2);      // 16 fp16 = 32 B = 2 x 16 B units
-            umma_f16(d1, d_ahi + ko, d_bhi + ko, idesc, (in_chunk > 0 || k > 0) ? 1u : 0u);
+            umma_f16(d1, d_ahi + ko, d_bhi + ko, idesc, (!first_of_chunk || k > 0) ? 1u : 0u);
             umma_f16(d2, d_ahi + ko, d_blo + ko, idesc, (it > item.k0 || k > 0) ? 1u : 0u);
             umma_f16(d2, d_alo + ko, d_bhi + ko, idesc, 1u);
           }
           umma_commit(&empty_bar[st]);                  // frees the smem slot once these MMAs retire
-          if (in_chunk == TC_CHUNK_STAGES - 1 || it == item.k1 - 1) {
+          if (rel + 1 == chunk_stop) {
             umma_commit(&acc_full_bar[buf]);            // D1[buf] (and, on the last chunk, D2[tbuf]) complete
             ++gchunk;
           }
@@ -456,7 +473,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
     TcItem item;
     for (; sched.next(item); ++tile_iter) {
       const int t = a.reverse ? total_tiles - 1 - item.tile : item.tile;    // coordinates only: the schedule is unchanged
-      const int n_acc_chunks = (item.k1 - item.k0 + TC_CHUNK_STAGES - 1) / TC_CHUNK_STAGES;
+      const int n_rel = item.k1 - item.k0;
       const int nt = t % a.n_tiles, mt = t / a.n_tiles;
       const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
       const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb;
@@ -479,7 +496,9 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
       float racc[HC];
 #pragma unroll
       for (int j = 0; j < HC; ++j) racc[j] = 0.f;
-      for (int c = 0; c < n_acc_chunks; ++c, ++gchunk) {
+      for (int rel = 0; rel < n_rel; ++gchunk) {
+        rel = tc_chunk_end(rel, n_rel, a.chunk_head, a.chunk_tail);
+        const bool last_chunk = rel >= n_rel;
         const uint32_t buf = gchunk & 1u;
         mbar_wait(&acc_full_bar[buf], (gchunk >> 1) & 1u);
         tc_fence_after();
@@ -493,7 +512,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
             for (int j = 0; j < 32; ++j) racc[ch * 32 + j] = __fadd_rn(racc[ch * 32 + j], __uint_as_float(r[j]));
           }
         }
-        if (c == n_acc_chunks - 1) {                     // the last commit also covers every D2 MMA of the tile
+        if (last_chunk) {                                // the last commit also covers every D2 MMA of the tile
 #pragma unroll
           for (int ch = 0; ch < HC / 32; ++ch) {
             if (n0 + ch * 32 < a.cout) {
@@ -913,6 +932,8 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   a.n_tiles = L.cout_pad / bn;
   a.stride = L.stride;
   a.reverse = io.reverse;
+  a.chunk_head = 2 * TC_CHUNK_STAGES;
+  a.chunk_tail = (io.chunk_tail >= 1 && io.chunk_tail <= TC_CHUNK_STAGES) ? io.chunk_tail : TC_CHUNK_STAGES;
   a.overflow = io.overflow_flag;
   const bool res_tma = io.res.hi != nullptr && bn == 128 && L.cout % 128 == 0 && !io.out_f32;
   // 16 epilogue warps for the short-K layers (<= 8 K stages per tile: their tile time is the epilogue)

@@ -116,6 +116,7 @@ struct lumi_engine {
   int* d_overflow = nullptr;
   ConvWorkspace sk_ws[2];       // stream-K scratch, one per stream
   int conv_streamk = 1;         // 0 off, 1 auto, 2 whenever possible
+  int conv_chunk_tail = 4;      // env LUMI_CONV_CHUNK_TAIL: D1 chunk length (stages) past the first eight stages of a tile
   int conv_epi16 = 0;           // env LUMI_CONV_EPI16: 16-epilogue-warp kernels for the short-K layers
   int conv_serpentine = 0;      // env LUMI_CONV_SERPENTINE: consecutive conv layers walk their tiles in opposite directions
   uint8_t* d_images = nullptr; size_t images_cap = 0;
@@ -646,6 +647,7 @@ Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* re
   io.streamk = cx.e->conv_streamk;
   io.sm_reserve = cx.sm_reserve;
   io.epi16 = cx.e->conv_epi16;
+  io.chunk_tail = cx.e->conv_chunk_tail;
   if (cx.e->conv_serpentine) { io.reverse = cx.conv_parity; cx.conv_parity ^= 1; }
   if (!cx.dry) {
     const bool tc = cx.e->conv_impl == 1 && conv_tc_supported(L, io);
@@ -1155,6 +1157,7 @@ int lumi_finalize(lumi_engine* e) {
   if (const char* v = std::getenv("LUMI_GRAPHS")) e->use_graphs = std::atoi(v) != 0;
   if (const char* v = std::getenv("LUMI_CONV_SERPENTINE")) e->conv_serpentine = std::atoi(v) != 0;
   if (const char* v = std::getenv("LUMI_CONV_EPI16")) e->conv_epi16 = std::atoi(v) != 0;
+  if (const char* v = std::getenv("LUMI_CONV_CHUNK_TAIL")) e->conv_chunk_tail = std::max(1, std::min(4, std::atoi(v)));
   if (e->max_batch >= 2) {
     conv_workspace_create(e->sk_ws[1]);
     LUMI_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));

@@ -32,6 +32,12 @@ timeout -s KILL 900 ncu --set full --clock-control none --import-source on --pro
 echo "ncu conv6 exit $?" >> gpurun_out/a_summary.txt
 timeout -s KILL 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:roi_pool -c 1 -f -o gpurun_out/a_prof_roi python bench.py --ncu-range --ncu-unpiped --no-cpu-baseline > gpurun_out/a_ncu_roi.log 2>&1
 echo "ncu roi exit $?" >> gpurun_out/a_summary.txt
+# D1 chunk schedule: accuracy (BASELINE-config parity report) and speed (bench --layers) at 1 / 2 stages per chunk
+for t in 2 1; do
+  LUMI_CONV_CHUNK_TAIL=$t LUMI_PARITY_TAG=_tail$t timeout -s KILL 900 python -m pytest tests/test_gpu_baseline_configs.py -m gpu -q -p no:cacheprovider -k "config2 or config4" --timeout 600 --timeout-method=thread > gpurun_out/a_pytest_tail$t.log 2>&1
+  echo "pytest tail$t exit $?" >> gpurun_out/a_summary.txt
+  LUMI_CONV_CHUNK_TAIL=$t timeout -s KILL 300 python bench.py --steps 20 --warmup 4 --layers --no-cpu-baseline > gpurun_out/a_bench_r50_tail$t.json 2>/dev/null
+done
 # LAST (new, untested kernels: a hang must not cost the rest of the call): 16-epilogue-warp conv kernels
 timeout -s KILL 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider -k "epi16" --timeout 120 --timeout-method=thread > gpurun_out/a_pytest_epi16.log 2>&1
 echo "pytest epi16 exit $?" >> gpurun_out/a_summary.txt
@@ -42,7 +48,7 @@ tail -n 8 gpurun_out/a_pytest_epi16.log
 cat gpurun_out/a_summary.txt
 python - <<'PY'
 import json
-for wl in ('r50','r50_roi_cells','r50_roi_cols8','r50_serp','r50_epi16','r50_graphs','r50_b1','r50_b1_graphs','r50_b2','r50_b2_graphs','ssd','r101'):
+for wl in ('r50','r50_roi_cells','r50_roi_cols8','r50_serp','r50_tail2','r50_tail1','r50_epi16','r50_graphs','r50_b1','r50_b1_graphs','r50_b2','r50_b2_graphs','ssd','r101'):
     try:
         d=json.load(open('gpurun_out/a_bench_%s.json'%wl)); print(wl, d['value'], d['ms_per_step'], d['e2e']['value'], d['category_ms_per_step'], d['roofline']['frac'])
     except Exception as e: print(wl, 'ERR', e)

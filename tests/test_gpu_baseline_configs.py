@@ -38,7 +38,7 @@ PX = 1e-3
 def _report(key, **vals):
     REPORT[key] = {k: (float(v) if not isinstance(v, (list, str)) else v) for k, v in vals.items()}
     os.makedirs('gpurun_out', exist_ok=True)
-    with open('gpurun_out/parity_report_baseline.json', 'w') as f:
+    with open('gpurun_out/parity_report_baseline%s.json' % os.environ.get('LUMI_PARITY_TAG', ''), 'w') as f:
         json.dump(REPORT, f, indent=1, sort_keys=True)
 
 
