@@ -439,6 +439,198 @@ __global__ void __launch_bounds__(32 * WARPS) roi_pool_cols_kernel(const RoiArgs
   }
 }
 
+
+// =====================================================================================================================
+// Row-walk kernel (round 2, second pass over the design).  ncu on the column-walk kernel above (profiles/r2_*): only
+// 28 % of its 1.12 G warp instructions were lerps / maxima / loads -- the rest was the warp-uniform bookkeeping of tap
+// sharing (compares, branches, register moves) -- and its L1 hit rate was 6 %: every tap is an L2 hit, so sharing
+// taps across samples does not save memory traffic that L1 would not merge anyway.  This kernel drops all
+// data-dependent sharing logic:
+//  * a sample's right / bottom tap is ALWAYS the next cell (offset +C / +row, or +0 on the last cell): when the
+//    coordinate is an exact integer TF uses floor == ceil, but its lerp weight is then 0, so the value is identical;
+//  * four sample columns (two pooled columns) per pass instead of two: half the passes over the rows;
+//  * the row plan (which sample rows reuse / shift / reload the two resident feature rows) is computed ONCE per warp
+//    into a 2-bit-per-row mask instead of being re-derived with compares in every pass;
+//  * 3 maxima per pooled cell instead of 4.
+// One warp = one ROI x 128 channels (4 per lane, LDG.128), no shared memory, no CTA barriers.
+// =====================================================================================================================
+template <int NC>
+__device__ __forceinline__ void roi_hrow(const float* f, int rowoff, const int (&xo)[NC], const int (&xd)[NC],
+                                         const float (&xt)[NC], RoiVec<4> (&H)[NC]) {
+  RoiVec<4> l[NC], r[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) l[j] = roi_load<4>(f, rowoff + xo[j]);
+#pragma unroll
+  for (int j = 0; j < NC; ++j) r[j] = roi_load<4>(f, rowoff + xo[j] + xd[j]);
+#pragma unroll
+  for (int j = 0; j < NC; ++j) H[j] = roi_lerp<4>(l[j], r[j], xt[j]);
+}
+
+__device__ __forceinline__ RoiVec<4> roi_vmax(const RoiVec<4>& a, const RoiVec<4>& b) {
+  RoiVec<4> m;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) { m.p[j].x = fmaxf(a.p[j].x, b.p[j].x); m.p[j].y = fmaxf(a.p[j].y, b.p[j].y); }
+  return m;
+}
+
+// One pass: sample columns [col0, col0 + NC) of the crop, all sample rows.  s_* are the lane-resident sample tables
+// (lane i < crop_h: y sample i; lane crop_h + j: x sample j): off = element offset of the low tap (row * fw*C or
+// col * C), dlt = distance to the high tap (one row / one pixel, 0 on the last cell), t = lerp weight, ok = inside.
+template <int NC>
+__device__ __forceinline__ void roi_rows_pass(const float* f, const RoiArgs& a, int col0, int s_off, int s_dlt, float s_t,
+                                              int s_ok, unsigned plan, int row, int c0, bool lane_ok, RoiVec<4>& msum) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int oh = a.crop_h >> 1, ow = a.crop_w >> 1;
+  int xo[NC], xd[NC], xk[NC];
+  float xt[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    const int ln = a.crop_h + col0 + j;
+    xo[j] = __shfl_sync(FULL, s_off, ln); xd[j] = __shfl_sync(FULL, s_dlt, ln);
+    xt[j] = __shfl_sync(FULL, s_t, ln); xk[j] = __shfl_sync(FULL, s_ok, ln);
+  }
+  // H0 / H1 hold the two resident feature rows; `parity` says which one currently plays "top".  A one-row advance
+  // (the common case: the crop's row step is below one cell for ROIs under 14 cells tall) flips the parity and
+  // overwrites the old top with the new bottom -- no register copies.
+  RoiVec<4> H0[NC], H1[NC], best[NC / 2];
+#pragma unroll
+  for (int j = 0; j < NC; ++j)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) H0[j].p[k] = H1[j].p[k] = make_float2(0.f, 0.f);
+  int parity = 0;
+  for (int py = 0; py < oh; ++py) {
+#pragma unroll
+    for (int sy = 0; sy < 2; ++sy) {
+      const int i = 2 * py + sy;
+      const unsigned act = (plan >> (2 * i)) & 3u;                  // 0 reuse, 1 advance one row, 2 load both, 3 outside
+      const int yo = __shfl_sync(FULL, s_off, i), yd = __shfl_sync(FULL, s_dlt, i);
+      const float ly = __shfl_sync(FULL, s_t, i);
+      if (act == 1u) parity ^= 1;
+      auto step = [&](RoiVec<4> (&T)[NC], RoiVec<4> (&B)[NC]) {
+        if (act == 1u) {
+          roi_hrow<NC>(f, yo + yd, xo, xd, xt, B);
+        } else if (act == 2u) {
+          roi_hrow<NC>(f, yo, xo, xd, xt, T);
+          roi_hrow<NC>(f, yo + yd, xo, xd, xt, B);
+        }
+        RoiVec<4> v[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          if (act != 3u && xk[j]) v[j] = roi_lerp<4>(T[j], B[j], ly);
+          else { v[j].p[0] = make_float2(0.f, 0.f); v[j].p[1] = make_float2(0.f, 0.f); }    // extrapolation_value = 0
+        }
+#pragma unroll
+        for (int m = 0; m < NC / 2; ++m) {
+          const RoiVec<4> mh = roi_vmax(v[2 * m], v[2 * m + 1]);
+          best[m] = sy == 0 ? mh : roi_vmax(best[m], mh);
+        }
+      };
+      if (parity == 0) step(H0, H1); else step(H1, H0);
+    }
+#pragma unroll
+    for (int m = 0; m < NC / 2; ++m) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) { msum.p[k].x += best[m].p[k].x; msum.p[k].y += best[m].p[k].y; }
+      if (a.ohi && lane_ok) {
+        const int q = (col0 >> 1) + m;
+        const size_t off = ((size_t)row * (oh * ow) + (size_t)py * ow + q) * a.c + c0;
+        __half2 vh[2], vl[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) split2_f32(best[m].p[k].x, best[m].p[k].y, vh[k], vl[k]);
+        *reinterpret_cast<uint2*>(a.ohi + off) = *reinterpret_cast<const uint2*>(vh);
+        *reinterpret_cast<uint2*>(a.olo + off) = *reinterpret_cast<const uint2*>(vl);
+      }
+    }
+  }
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) roi_pool_rows_kernel(const RoiArgs a) {
+  constexpr int CPL = 4, SLICE = 32 * CPL;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x;                                   // global roi row = img * rmax + r
+  const int slice = blockIdx.y * WARPS + warp;
+  if (slice * SLICE >= a.c) return;                             // whole warp
+  const int c0 = slice * SLICE + lane * CPL;
+  const bool lane_ok = c0 < a.c;
+  const int img = row / a.rmax, r = row - img * a.rmax;
+  const int oh = a.crop_h >> 1, ow = a.crop_w >> 1;
+  const int ncell = oh * ow;
+  const bool live = (a.counts == nullptr || r < a.counts[img]);
+  if (!live) {                                                  // padded row: zeros (the heads read every row)
+    if (lane_ok) {
+      const uint2 z = make_uint2(0u, 0u);
+      if (a.ohi)
+        for (int cell = 0; cell < ncell; ++cell) {
+          const size_t off = ((size_t)row * ncell + cell) * a.c + c0;
+          *reinterpret_cast<uint2*>(a.ohi + off) = z; *reinterpret_cast<uint2*>(a.olo + off) = z;
+        }
+      if (a.mhi) {
+        *reinterpret_cast<uint2*>(a.mhi + (size_t)row * a.c + c0) = z;
+        *reinterpret_cast<uint2*>(a.mlo + (size_t)row * a.c + c0) = z;
+      }
+    }
+    return;
+  }
+  // ---- sample tables (TF crop_and_resize arithmetic in the reference's operation order, quirk Q3)
+  const int rowstride = a.fw * a.c;
+  int s_off = 0, s_dlt = 0, s_ok = 0, s_cell = 0;
+  float s_t = 0.f;
+  if (lane < a.crop_h + a.crop_w) {
+    const bool is_y = lane < a.crop_h;
+    const int k = is_y ? lane : lane - a.crop_h;
+    const float* rb = a.rois + (size_t)row * 4;
+    const float lo_n = is_y ? __fdiv_rn(rb[1], a.im_h) : __fdiv_rn(rb[0], a.im_w);
+    const float hi_n = is_y ? __fdiv_rn(rb[3], a.im_h) : __fdiv_rn(rb[2], a.im_w);
+    const int crop = is_y ? a.crop_h : a.crop_w;
+    const int D = is_y ? a.fh : a.fw;
+    const float Dm1 = (float)(D - 1);
+    const float step = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(hi_n, lo_n), Dm1), (float)(crop - 1)) : 0.f;
+    const float in = crop > 1 ? __fadd_rn(__fmul_rn(lo_n, Dm1), __fmul_rn((float)k, step))
+                              : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(lo_n, hi_n)), Dm1);
+    s_ok = !(in < 0.f || in > Dm1);
+    s_cell = s_ok ? (int)floorf(in) : 0;
+    s_t = __fsub_rn(in, (float)s_cell);            // == 0 exactly when in is an integer: the high tap's value is unused
+    const int unit = is_y ? rowstride : a.c;
+    s_off = s_cell * unit;
+    s_dlt = (s_cell < D - 1) ? unit : 0;
+  }
+  // ---- row plan, once per warp: which of the two resident feature rows each sample row can reuse
+  unsigned plan = 0u;
+  {
+    int cur_top = -1, cur_bot = -1;
+    for (int i = 0; i < a.crop_h; ++i) {
+      const int cell = __shfl_sync(FULL, s_cell, i), ok = __shfl_sync(FULL, s_ok, i), dl = __shfl_sync(FULL, s_dlt, i);
+      unsigned act;
+      if (!ok) act = 3u;
+      else {
+        const int lo = cell, hi = cell + (dl != 0);
+        if (lo == cur_top && hi == cur_bot) act = 0u;
+        else if (lo == cur_bot && cur_bot != cur_top) { act = 1u; cur_top = lo; cur_bot = hi; }
+        else { act = 2u; cur_top = lo; cur_bot = hi; }
+      }
+      plan |= act << (2 * i);
+    }
+  }
+  const float* f = a.fmap + (size_t)img * a.fh * a.fw * a.c + (lane_ok ? c0 : 0);
+  asm volatile("" : "+l"(f));     // keep ONE per-lane base pointer: every tap address is then base + 32-bit offset
+  RoiVec<4> msum;
+  msum.p[0] = msum.p[1] = make_float2(0.f, 0.f);
+  int col0 = 0;
+  for (; col0 + 4 <= a.crop_w; col0 += 4) roi_rows_pass<4>(f, a, col0, s_off, s_dlt, s_t, s_ok, plan, row, c0, lane_ok, msum);
+  if (col0 < a.crop_w) roi_rows_pass<2>(f, a, col0, s_off, s_dlt, s_t, s_ok, plan, row, c0, lane_ok, msum);
+  if (a.mhi && lane_ok) {            // fused tf.reduce_mean over the pooled cells (rcnn.py:188)
+    __half2 vh[2], vl[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      split2_f32(__fdiv_rn(msum.p[k].x, (float)ncell), __fdiv_rn(msum.p[k].y, (float)ncell), vh[k], vl[k]);
+    const size_t off = (size_t)row * a.c + c0;
+    *reinterpret_cast<uint2*>(a.mhi + off) = *reinterpret_cast<const uint2*>(vh);
+    *reinterpret_cast<uint2*>(a.mlo + off) = *reinterpret_cast<const uint2*>(vl);
+  }
+}
+
 void launch_roi_pool(const float* fmap_f32, int n, int fh, int fw, int c, const float* rois, const int* counts, int rmax,
                      float im_h, float im_w, int ph, int pw, Act out, Act mean, cudaStream_t st) {
   LUMI_REQUIRE(c % 8 == 0, "roi_pool: C must be a multiple of 8");
@@ -452,8 +644,23 @@ void launch_roi_pool(const float* fmap_f32, int n, int fh, int fw, int c, const 
   LUMI_REQUIRE(out.hi || mean.hi, "roi_pool: no output requested");
   long rows = (long)n * rmax;
   if (!rows) return;
-  // LUMI_ROI_KERNEL: "cols" (default, round-2 column-walk kernel) | "cells" (round-1 kernel, kept for A/B measurement)
-  static const int variant = [] { const char* e = getenv("LUMI_ROI_KERNEL"); return (e && e[0] == 'c' && e[1] == 'e') ? 0 : 1; }();
+  // LUMI_ROI_KERNEL: "rows" (default, round-2 row-walk kernel) | "cols" (round-2 first design) | "cells" (round-1 kernel);
+  // the older ones are kept for A/B measurement
+  static const int variant = [] {
+    const char* e = getenv("LUMI_ROI_KERNEL");
+    if (e && e[0] == 'c' && e[1] == 'e') return 0;
+    if (e && e[0] == 'c' && e[1] == 'o') return 1;
+    return 2;
+  }();
+  if (variant == 2 && a.crop_h <= 16 && a.crop_h + a.crop_w <= 32 && (a.crop_h & 1) == 0 && (a.crop_w & 1) == 0 &&
+      c % 4 == 0) {
+    constexpr int W = 4;
+    dim3 grid((unsigned)rows, (unsigned)cdiv(c, 128 * W));
+    roi_pool_rows_kernel<W><<<grid, 32 * W, 0, st>>>(a);
+    count_launch();
+    LUMI_CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   static const int cols_cpl = [] { const char* e = getenv("LUMI_ROI_COLS_CPL"); return (e && atoi(e) == 8) ? 8 : 4; }();
   if (variant == 1 && a.crop_h + a.crop_w <= 32 && (a.crop_h & 1) == 0 && (a.crop_w & 1) == 0 && c % cols_cpl == 0) {
     constexpr int W = 4;

@@ -102,19 +102,25 @@ def _frcnn_case(key, arch, overrides, batch_seed, picks):
                      fmap_rel_oracle32_vs_oracle64=rel_err(ref['conv_feature_map'][0], tru['conv_feature_map'][0]),
                      proposals_engine=int(pcnt[i]), proposals_oracle32=len(ref['rpn_prediction']['proposals']))
         rp = ref['rpn_prediction']['proposals']
-        if pcnt[i] == len(rp):
-            z = np.zeros(len(rp), int)
-            extra['proposals_px_engine_vs_oracle32'] = box_dev(props[i, :pcnt[i]], z, rp, z)
-            tp = tru['rpn_prediction']['proposals']
-            if len(tp) == len(rp):
-                extra['proposals_px_oracle32_vs_oracle64'] = box_dev(rp, z, tp, z)
+        # proposals are an ordered list: compare row by row; a near-threshold NMS decision that differs between two
+        # fp32 evaluations shifts the tail of the list, so report how many rows are within 1 px of their counterpart
+        # and the deviation over those
+        def rowwise(a_, b_):
+            n_ = min(len(a_), len(b_))
+            d_ = np.abs(a_[:n_].astype(np.float64) - b_[:n_]).max(axis=1) if n_ else np.zeros(0)
+            same = d_ <= 1.0
+            return float(same.sum()), float(d_[same].max() if same.any() else 0.0)
+        tp = tru['rpn_prediction']['proposals']
+        extra['proposals_rows_matching_engine_vs_oracle32'], extra['proposals_px_engine_vs_oracle32'] = rowwise(props[i, :pcnt[i]], rp)
+        extra['proposals_rows_matching_oracle32_vs_oracle64'], extra['proposals_px_oracle32_vs_oracle64'] = rowwise(rp, tp)
         k = int(counts[i])
         r = _det_compare('%s/img%d' % (key, i), boxes[i], scores[i], labels[i], k, ref['classification_prediction'],
                          tru['classification_prediction'], extra)
         # the single-stream debug run of the same batch agrees with the production run (stream-K split points
         # depend on the half-batch: fp32-noise differences only)
         assert int(tc[i]) == k
-        assert box_dev(tb[i, :k], tl[i, :k], boxes[i, :k], labels[i, :k]) <= 2e-3
+        noise = r.get('boxes_px_oracle32_vs_oracle64', 0.0)
+        assert box_dev(tb[i, :k], tl[i, :k], boxes[i, :k], labels[i, :k]) <= max(2e-3, 2.0 * noise)
         results.append((i, r))
     eng.close()
     for i, r in results:
