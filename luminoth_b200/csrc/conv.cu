@@ -271,16 +271,14 @@ constexpr int TC_CHUNK_STAGES = 4;          // 16 hi*hi MMAs per D1 chunk (the f
 // truncating accumulator): 16 MMAs ~5e-7 relative per layer, 8 ~2.8e-7, 4 ~1.8e-7; fp32 FMA chains of a CPU
 // conv sit at ~2e-7.
 __device__ __forceinline__ int tc_chunk_end(int rel, int n_rel, int head, int tail) {
-  const int len = rel < head ? TC_CHUNK_STAGES : tail;
+  // short work items (<= 4 stages: the 1x1 layers with C_in <= 256) fit the two D1 buffers whole, so they can use
+  // 1- or 2-stage chunks without shortening the MMA issuer's lead over the epilogue
+  const int head_len = n_rel <= 2 ? 1 : (n_rel <= 4 ? 2 : TC_CHUNK_STAGES);
+  const int len = rel < head ? head_len : tail;
   const int e = rel + len;
   return e < n_rel ? e : n_rel;
 }
 
-// NSPLIT: column parts of the epilogue (4 warps = 4 TMEM lane quadrants per part): 2 -> 8 epilogue warps (long-K layers),
-// 4 -> 16 epilogue warps for the short-K layers whose tile time IS the epilogue (1x1 convs of block1/2/3: one to eight
-// K stages per tile against ~3.5 us of drain + BN + residual + split + store on 8 warps).
-// INPLACE (RES kernels with one 32-channel slab per part): the residual tile is TMA-loaded INTO the part's output
-// staging slab, updated in place and stored from there, so residual + staging cost 64 KB instead of 128 KB.
 template <int BN, int STAGES, bool RES = false, int NSPLIT = 2, bool INPLACE = false>
 struct TcCfg {
   static_assert((BN / NSPLIT) % 32 == 0, "each epilogue part owns whole 32-channel slabs");
@@ -936,8 +934,10 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   a.chunk_tail = (io.chunk_tail >= 1 && io.chunk_tail <= TC_CHUNK_STAGES) ? io.chunk_tail : TC_CHUNK_STAGES;
   a.overflow = io.overflow_flag;
   const bool res_tma = io.res.hi != nullptr && bn == 128 && L.cout % 128 == 0 && !io.out_f32;
-  // 16 epilogue warps for the short-K layers (<= 8 K stages per tile: their tile time is the epilogue)
-  const bool epi16 = io.epi16 && bn == 128 && !io.out_f32 && (long)L.kh * L.kw * (L.cin >> 6) <= 8;
+  // 16 epilogue warps for the shortest-K layers (io.epi16 = largest K-stage count that uses them; measured per layer,
+  // profiles/r2_conv_variants.txt: they win on one-stage tiles (C_in = 64) and lose from four stages up, where their
+  // two operand stages cost more than the faster epilogue gains)
+  const bool epi16 = io.epi16 && bn == 128 && !io.out_f32 && (long)L.kh * L.kw * (L.cin >> 6) <= io.epi16;
   if (res_tma) {          // residual tile prefetched by TMA (box over the unit's input, subsampled by res_stride)
     a.tm_r_hi = cached_out_map(io.res.hi, io.res.n, io.res.h, io.res.w, io.res.c, nb, th, tw, io.res_stride);
     a.tm_r_lo = cached_out_map(io.res.lo, io.res.n, io.res.h, io.res.w, io.res.c, nb, th, tw, io.res_stride);

@@ -50,8 +50,8 @@ struct ConvIO {
   int streamk = 1;              // stream-K policy of THIS launch: 0 off, 1 auto (wave-quantisation heuristic), 2 whenever possible
   int reverse = 0;              // walk output tiles last-to-first: with the previous layer walking first-to-last, this
                                 // layer starts on the activations that are still resident in L2 (serpentine order)
-  int chunk_tail = 4;           // stages per D1 chunk after the first eight stages of a tile (1, 2 or 4; see tc_chunk_end)
-  int epi16 = 0;                // allow the 16-epilogue-warp kernels on short-K layers (A/B switch, env LUMI_CONV_EPI16)
+  int chunk_tail = 2;           // stages per D1 chunk after the first eight stages of a tile (1, 2 or 4; see tc_chunk_end)
+  int epi16 = 0;                // 16-epilogue-warp kernels on layers with at most this many K stages per tile (0 = never)
   int sm_reserve = 0;           // SMs a persistent launch leaves free (the engine's two-stream pipeline sets 8)
   // Optional strided ("Toeplitz") view of the input for the tcgen05 path: element pitches between
   // consecutive pixels / rows / images (0 = dense NHWC).  Used by the space-to-depth stem, where each

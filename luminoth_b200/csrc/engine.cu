@@ -116,8 +116,8 @@ struct lumi_engine {
   int* d_overflow = nullptr;
   ConvWorkspace sk_ws[2];       // stream-K scratch, one per stream
   int conv_streamk = 1;         // 0 off, 1 auto, 2 whenever possible
-  int conv_chunk_tail = 4;      // env LUMI_CONV_CHUNK_TAIL: D1 chunk length (stages) past the first eight stages of a tile
-  int conv_epi16 = 0;           // env LUMI_CONV_EPI16: 16-epilogue-warp kernels for the short-K layers
+  int conv_chunk_tail = 2;      // env LUMI_CONV_CHUNK_TAIL: D1 chunk length (stages) past the first eight stages of a tile
+  int conv_epi16 = 1;           // env LUMI_CONV_EPI16: 16-epilogue-warp kernels for tiles of at most this many K stages
   int conv_serpentine = 0;      // env LUMI_CONV_SERPENTINE: consecutive conv layers walk their tiles in opposite directions
   uint8_t* d_images = nullptr; size_t images_cap = 0;
   float* d_boxes = nullptr; float* d_scores = nullptr; int* d_labels = nullptr; int* d_counts = nullptr;
@@ -606,6 +606,12 @@ NmsWorkspace ws_view(const NmsWorkspace& ws, int off) {
   v.keep = ws.keep + (size_t)off * ws.max_out;
   v.nkeep = ws.nkeep + off;
   v.sort_tmp = ws.sort_tmp + (size_t)off * 2 * ws.cap;
+  if (ws.sboxes2) {
+    v.sboxes2 = ws.sboxes2 + (size_t)off * ws.ncap * 4;
+    v.index_map = ws.index_map + (size_t)off * ws.ncap;
+    v.alive = ws.alive + (size_t)off * ws.ncap;
+    v.nvalid2 = ws.nvalid2 + off;
+  }
   return v;
 }
 
@@ -1156,7 +1162,7 @@ int lumi_finalize(lumi_engine* e) {
   if (const char* v = std::getenv("LUMI_CONV_STREAMK")) e->conv_streamk = std::max(0, std::min(2, std::atoi(v)));
   if (const char* v = std::getenv("LUMI_GRAPHS")) e->use_graphs = std::atoi(v) != 0;
   if (const char* v = std::getenv("LUMI_CONV_SERPENTINE")) e->conv_serpentine = std::atoi(v) != 0;
-  if (const char* v = std::getenv("LUMI_CONV_EPI16")) e->conv_epi16 = std::atoi(v) != 0;
+  if (const char* v = std::getenv("LUMI_CONV_EPI16")) e->conv_epi16 = std::max(0, std::min(8, std::atoi(v)));
   if (const char* v = std::getenv("LUMI_CONV_CHUNK_TAIL")) e->conv_chunk_tail = std::max(1, std::min(4, std::atoi(v)));
   if (e->max_batch >= 2) {
     conv_workspace_create(e->sk_ws[1]);

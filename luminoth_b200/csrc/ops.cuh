@@ -42,6 +42,11 @@ struct NmsWorkspace {
   int* nkeep = nullptr;         // [P]
   int max_out = 0;
   unsigned long long* sort_tmp = nullptr;  // global-memory sort scratch for cap > 32768
+  // two-phase NMS (ncap >= 4096): survivors of the pre-filter, compacted in order
+  float* sboxes2 = nullptr;     // [P][ncap][4]
+  int* index_map = nullptr;     // [P][ncap]  compacted row -> row of sboxes
+  unsigned char* alive = nullptr;  // [P][ncap]
+  int* nvalid2 = nullptr;       // [P]
 };
 void nms_workspace_alloc(NmsWorkspace& ws, int problems, int cap, int max_out, int ncap = 0);
 void nms_workspace_free(NmsWorkspace& ws);

@@ -91,7 +91,7 @@ int lumi_op_conv2d(const float* x, int n, int h, int w, int cin, const float* wg
       split_out.reset(new ActBuf(n, ho, wo, cout));
       io.out = split_out->a;
       io.out_f32 = nullptr;
-      io.epi16 = impl >= 4;
+      io.epi16 = impl >= 4 ? 8 : 0;
     }
     LUMI_REQUIRE(conv_tc_supported(L, io), "conv2d: this layer shape is not handled by the tensor-core kernel");
     ConvWorkspace sk;

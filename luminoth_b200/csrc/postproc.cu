@@ -11,6 +11,7 @@
 // round-to-nearest intrinsics (no FMA contraction): discrete decisions
 // (>=, >, iou > thr) must agree with the fp32 reference bit for bit on equal inputs.
 #include "ops.cuh"
+#include <cstdlib>
 
 namespace lumi {
 
@@ -82,10 +83,17 @@ void nms_workspace_alloc(NmsWorkspace& ws, int problems, int cap, int max_out, i
   LUMI_CUDA_CHECK(cudaMalloc(&ws.keep, (size_t)problems * max_out * sizeof(int)));
   LUMI_CUDA_CHECK(cudaMalloc(&ws.nkeep, problems * sizeof(int)));
   LUMI_CUDA_CHECK(cudaMalloc(&ws.sort_tmp, (size_t)problems * 2 * cap * sizeof(unsigned long long)));   // radix ping-pong
+  if (ncap >= 4096) {                       // two-phase NMS scratch (see run_nms)
+    LUMI_CUDA_CHECK(cudaMalloc(&ws.sboxes2, pn * 4 * sizeof(float)));
+    LUMI_CUDA_CHECK(cudaMalloc(&ws.index_map, pn * sizeof(int)));
+    LUMI_CUDA_CHECK(cudaMalloc(&ws.alive, pn));
+    LUMI_CUDA_CHECK(cudaMalloc(&ws.nvalid2, problems * sizeof(int)));
+  }
 }
 void nms_workspace_free(NmsWorkspace& ws) {
   cudaFree(ws.keys); cudaFree(ws.boxes); cudaFree(ws.order); cudaFree(ws.nvalid); cudaFree(ws.sboxes);
   cudaFree(ws.sscores); cudaFree(ws.mask); cudaFree(ws.keep); cudaFree(ws.nkeep); cudaFree(ws.sort_tmp);
+  cudaFree(ws.sboxes2); cudaFree(ws.index_map); cudaFree(ws.alive); cudaFree(ws.nvalid2);
   ws = NmsWorkspace();
 }
 
@@ -289,9 +297,9 @@ __device__ __noinline__ bool iou_exact_gt(float inter, float uni, float thr) {
 // almost every pair, the IEEE divide only runs for ratios within the margin of the threshold.
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sboxes, const int* __restrict__ nvalid,
                                                       int cap, int words, float thr,
-                                                      unsigned long long* __restrict__ mask) {
+                                                      unsigned long long* __restrict__ mask, int limit) {
   const int p = blockIdx.y;
-  const int n = nvalid[p];
+  const int n = min(nvalid[p], limit);                // limit: only the first `limit` candidates (two-phase NMS)
   const int nw = (n + 63) >> 6;
   const long npairs = (long)nw * (nw + 1) / 2;
   __shared__ float4 cbox[64];        // raw boxes (generic path)
@@ -451,10 +459,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// limit: scan only the first `limit` candidates.  base_count / index_map (second phase of the two-phase NMS): the
+// keep list already holds base_count[p] entries, and candidate r of THIS scan is index_map[p][r] of the original list.
 __global__ void __launch_bounds__(256) nms_scan_staged_kernel(const unsigned long long* __restrict__ mask,
                                                               const int* __restrict__ nvalid, int cap, int words,
                                                               int max_out, int* __restrict__ keep,
-                                                              int* __restrict__ nkeep) {
+                                                              int* __restrict__ nkeep, int limit,
+                                                              const int* __restrict__ base_count,
+                                                              const int* __restrict__ index_map) {
   extern __shared__ __align__(16) unsigned long long sm64[];
   unsigned long long* removed = sm64;                         // [words]
   unsigned long long* buf = sm64 + words;                     // [2][64][words]
@@ -462,12 +474,14 @@ __global__ void __launch_bounds__(256) nms_scan_staged_kernel(const unsigned lon
   __shared__ int s_kept[64];
   __shared__ int s_nk, s_total, s_done;
   const int p = blockIdx.x;
-  const int n = nvalid[p];
+  const int n = min(nvalid[p], limit);
   const int nw = (n + 63) >> 6;
   const unsigned long long* M = mask + (size_t)p * cap * words;
+  const int* imap = index_map ? index_map + (size_t)p * cap : nullptr;
   for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = 0ull;
   if (threadIdx.x == 0) {
-    s_total = 0; s_done = (max_out <= 0 || n == 0) ? 1 : 0;
+    s_total = base_count ? base_count[p] : 0;
+    s_done = (max_out <= 0 || n == 0 || s_total >= max_out) ? 1 : 0;
     mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
     fence_mbar_init();
   }
@@ -503,7 +517,7 @@ __global__ void __launch_bounds__(256) nms_scan_staged_kernel(const unsigned lon
       while (avail) {
         const int b = __ffsll((long long)avail) - 1;
         s_kept[nk++] = b;
-        keep[(size_t)p * max_out + total] = c * 64 + b;
+        keep[(size_t)p * max_out + total] = imap ? imap[c * 64 + b] : c * 64 + b;
         if (++total >= max_out) { s_done = 1; break; }
         cur |= rows[(size_t)b * words + c];
         avail = ~cur & vmask & ~((2ull << b) - 1ull);
@@ -525,39 +539,153 @@ __global__ void __launch_bounds__(256) nms_scan_staged_kernel(const unsigned lon
   if (threadIdx.x == 0) nkeep[p] = s_total;
 }
 
-static void run_nms(NmsWorkspace& ws, int problems, float thr, int max_out, cudaStream_t st) {
-  if (!problems) return;
+// ---- two-phase ("lazy") NMS for long candidate lists.
+// The bit-mask matrix costs N^2/2 pair tests although the greedy scan only ever reads the rows of KEPT boxes.  Phase 1
+// resolves the first R1 candidates exactly as before (mask + scan on an R1 x R1 triangle).  A pre-filter then tests
+// every later candidate against those kept boxes only (k1 x (N - R1) pairs) and the survivors -- the only later
+// candidates that can still be kept -- are compacted in order; phase 2 runs mask + scan on the survivors and appends to
+// the keep list through the index map.  Kept set and order are identical to the one-phase result (a candidate
+// suppressed by a phase-1 keeper is suppressed in the greedy walk as well, and suppression among later candidates
+// involves survivors only); the pair tests drop from N^2/2 to R1^2/2 + k1 (N - R1) + S^2/2.
+constexpr int NMS_LAZY_R1 = 2048;
+constexpr int NMS_LAZY_MIN = 4096;
+
+__global__ void __launch_bounds__(256) nms_prefilter_kernel(const float* __restrict__ sboxes,
+                                                            const int* __restrict__ nvalid, int cap, float thr,
+                                                            const int* __restrict__ keep, const int* __restrict__ nkeep,
+                                                            int max_out, int r1, unsigned char* __restrict__ alive) {
+  const int p = blockIdx.y;
+  const int n = nvalid[p];
+  const int k1 = nkeep[p];
+  const int j = r1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r1 + (int)(blockIdx.x * blockDim.x) >= n || k1 >= max_out) return;        // whole block: nothing left to decide
+  __shared__ NBox kb[256];
+  const float4* B = reinterpret_cast<const float4*>(sboxes) + (size_t)p * cap;
+  const bool mine = j < n;
+  const NBox me = normalise_box(mine ? B[j] : make_float4(0.f, 0.f, 0.f, 0.f));
+  bool dead = false;
+  for (int base = 0; base < k1; base += 256) {
+    __syncthreads();
+    if (base + (int)threadIdx.x < k1) kb[threadIdx.x] = normalise_box(B[keep[(size_t)p * max_out + base + threadIdx.x]]);
+    __syncthreads();
+    const int m = min(256, k1 - base);
+    if (mine && !dead)
+      for (int i = 0; i < m; ++i)
+        if (iou_gt_norm(kb[i], me, thr)) { dead = true; break; }
+  }
+  if (mine) alive[(size_t)p * cap + j] = dead ? 0 : 1;
+}
+
+// stable compaction of the survivors of candidates [r1, n): one CTA per problem
+__global__ void __launch_bounds__(1024) nms_compact_kernel(const float* __restrict__ sboxes, const int* __restrict__ nvalid,
+                                                           int cap, const unsigned char* __restrict__ alive,
+                                                           const int* __restrict__ nkeep, int max_out, int r1,
+                                                           float* __restrict__ sboxes2, int* __restrict__ index_map,
+                                                           int* __restrict__ nvalid2) {
+  const int p = blockIdx.x;
+  const int n = nvalid[p];
+  __shared__ int warp_tot[32];
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  const bool finished = nkeep[p] >= max_out;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4* B = reinterpret_cast<const float4*>(sboxes) + (size_t)p * cap;
+  float4* B2 = reinterpret_cast<float4*>(sboxes2) + (size_t)p * cap;
+  __syncthreads();
+  if (!finished)
+    for (int base = r1; base < n; base += 1024) {       // uniform trip count
+      const int j = base + threadIdx.x;
+      const int a = (j < n && alive[(size_t)p * cap + j]) ? 1 : 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, a);
+      const int rank = __popc(bal & ((1u << lane) - 1u));
+      if (lane == 0) warp_tot[warp] = __popc(bal);
+      __syncthreads();
+      int woff = 0, tot = 0;
+      for (int w = 0; w < 32; ++w) { const int t = warp_tot[w]; if (w < warp) woff += t; tot += t; }
+      const int start = s_base;
+      if (a) {
+        const int dst = start + woff + rank;
+        B2[dst] = B[j];
+        index_map[(size_t)p * cap + dst] = j;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) s_base = start + tot;
+      __syncthreads();
+    }
+  if (threadIdx.x == 0) nvalid2[p] = finished ? 0 : s_base;
+}
+
+static void launch_scan_staged(NmsWorkspace& ws, const unsigned long long* mask, const int* nvalid, int problems,
+                               int max_out, int limit, const int* base_count, const int* index_map, cudaStream_t st) {
+  const size_t staged_smem = ((size_t)ws.words + 2 * 64 * (size_t)ws.words) * sizeof(unsigned long long);
+  static bool attr[64] = {false};        // cudaFuncSetAttribute is per device
+  int dev = 0;
+  LUMI_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !__atomic_load_n(&attr[dev], __ATOMIC_ACQUIRE)) {
+    LUMI_CUDA_CHECK(cudaFuncSetAttribute(nms_scan_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024));
+    if (dev >= 0 && dev < 64) __atomic_store_n(&attr[dev], true, __ATOMIC_RELEASE);
+  }
+  nms_scan_staged_kernel<<<problems, 256, staged_smem, st>>>(mask, nvalid, ws.ncap, ws.words, max_out, ws.keep, ws.nkeep,
+                                                            limit, base_count, index_map);
+  count_launch();
+  LUMI_CUDA_CHECK(cudaGetLastError());
+}
+
+static dim3 mask_grid(const NmsWorkspace& ws, int problems, int n_max) {
   // blocks walk their problem's (row block, column block) pairs with a grid stride; the x extent is sized so that
   // the whole launch is ~64 resident blocks per SM -- with hundreds of (image, class) problems whose candidate
   // lists are short (SSD: 640 problems, most rows filtered by min_prob) a fixed 2048-wide grid was 1.3 M blocks
   // that exit at once: 0.68 ms of block-launch overhead per step (ncu, profiles/r2_ncu_step_summary.json)
-  long maxpairs = (long)ws.words * (ws.words + 1) / 2;
+  const long nw = (n_max + 63) / 64;
+  long maxpairs = nw * (nw + 1) / 2;
   long gx = (148L * 64 + problems - 1) / problems;
   if (gx > 2048) gx = 2048;
   if (gx > maxpairs) gx = maxpairs;
   if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, problems);
-  nms_mask_kernel<<<grid, 64, 0, st>>>(ws.sboxes, ws.nvalid, ws.ncap, ws.words, thr, ws.mask);
+  (void)ws;
+  return dim3((unsigned)gx, problems);
+}
+
+static void run_nms(NmsWorkspace& ws, int problems, float thr, int max_out, cudaStream_t st) {
+  if (!problems) return;
+  const size_t staged_smem = ((size_t)ws.words + 2 * 64 * (size_t)ws.words) * sizeof(unsigned long long);
+  const bool staged = staged_smem <= 200 * 1024;
+  static const bool lazy_on = [] { const char* e = getenv("LUMI_NMS_LAZY"); return e && atoi(e) != 0; }();   // opt-in until validated
+  const bool lazy = lazy_on && staged && ws.sboxes2 && ws.ncap >= NMS_LAZY_MIN && thr > 0.f && thr < INFINITY;
+  if (lazy) {
+    const int R1 = NMS_LAZY_R1;
+    nms_mask_kernel<<<mask_grid(ws, problems, R1), 64, 0, st>>>(ws.sboxes, ws.nvalid, ws.ncap, ws.words, thr, ws.mask, R1);
+    count_launch();
+    LUMI_CUDA_CHECK(cudaGetLastError());
+    launch_scan_staged(ws, ws.mask, ws.nvalid, problems, max_out, R1, nullptr, nullptr, st);
+    dim3 gp((unsigned)cdiv(ws.ncap - R1, 256), problems);
+    nms_prefilter_kernel<<<gp, 256, 0, st>>>(ws.sboxes, ws.nvalid, ws.ncap, thr, ws.keep, ws.nkeep, max_out, R1, ws.alive);
+    count_launch();
+    LUMI_CUDA_CHECK(cudaGetLastError());
+    nms_compact_kernel<<<problems, 1024, 0, st>>>(ws.sboxes, ws.nvalid, ws.ncap, ws.alive, ws.nkeep, max_out, R1,
+                                                  ws.sboxes2, ws.index_map, ws.nvalid2);
+    count_launch();
+    LUMI_CUDA_CHECK(cudaGetLastError());
+    nms_mask_kernel<<<mask_grid(ws, problems, ws.ncap - R1), 64, 0, st>>>(ws.sboxes2, ws.nvalid2, ws.ncap, ws.words, thr,
+                                                                         ws.mask, 0x7fffffff);
+    count_launch();
+    LUMI_CUDA_CHECK(cudaGetLastError());
+    launch_scan_staged(ws, ws.mask, ws.nvalid2, problems, max_out, 0x7fffffff, ws.nkeep, ws.index_map, st);
+    return;
+  }
+  nms_mask_kernel<<<mask_grid(ws, problems, ws.ncap), 64, 0, st>>>(ws.sboxes, ws.nvalid, ws.ncap, ws.words, thr, ws.mask,
+                                                                  0x7fffffff);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
-  const size_t staged_smem = ((size_t)ws.words + 2 * 64 * (size_t)ws.words) * sizeof(unsigned long long);
-  if (staged_smem <= 200 * 1024) {
-    static bool attr[64] = {false};        // cudaFuncSetAttribute is per device
-    int dev = 0;
-    LUMI_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !__atomic_load_n(&attr[dev], __ATOMIC_ACQUIRE)) {
-      LUMI_CUDA_CHECK(cudaFuncSetAttribute(nms_scan_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           200 * 1024));
-      if (dev >= 0 && dev < 64) __atomic_store_n(&attr[dev], true, __ATOMIC_RELEASE);
-    }
-    nms_scan_staged_kernel<<<problems, 256, staged_smem, st>>>(ws.mask, ws.nvalid, ws.ncap, ws.words, max_out, ws.keep,
-                                                              ws.nkeep);
+  if (staged) {
+    launch_scan_staged(ws, ws.mask, ws.nvalid, problems, max_out, 0x7fffffff, nullptr, nullptr, st);
   } else {
     size_t smem = (size_t)ws.words * sizeof(unsigned long long);
     nms_scan_kernel<<<problems, 256, smem, st>>>(ws.mask, ws.nvalid, ws.ncap, ws.words, max_out, ws.keep, ws.nkeep);
+    count_launch();
+    LUMI_CUDA_CHECK(cudaGetLastError());
   }
-  count_launch();
-  LUMI_CUDA_CHECK(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------ RPN chain

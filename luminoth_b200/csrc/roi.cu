@@ -544,8 +544,8 @@ __device__ __forceinline__ void roi_rows_pass(const float* f, const RoiArgs& a, 
   }
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(32 * WARPS) roi_pool_rows_kernel(const RoiArgs a) {
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB) roi_pool_rows_kernel(const RoiArgs a) {
   constexpr int CPL = 4, SLICE = 32 * CPL;
   constexpr unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -656,7 +656,11 @@ void launch_roi_pool(const float* fmap_f32, int n, int fh, int fw, int c, const 
       c % 4 == 0) {
     constexpr int W = 4;
     dim3 grid((unsigned)rows, (unsigned)cdiv(c, 128 * W));
-    roi_pool_rows_kernel<W><<<grid, 32 * W, 0, st>>>(a);
+    // occupancy A/B: 4 / 5 / 6 resident CTAs per SM (<= 128 / 102 / 80 registers)
+    static const int minb = [] { const char* e = getenv("LUMI_ROI_MINB"); const int v = e ? atoi(e) : 5; return (v == 4 || v == 6) ? v : 5; }();
+    if (minb == 6) roi_pool_rows_kernel<W, 6><<<grid, 32 * W, 0, st>>>(a);
+    else if (minb == 4) roi_pool_rows_kernel<W, 4><<<grid, 32 * W, 0, st>>>(a);
+    else roi_pool_rows_kernel<W, 5><<<grid, 32 * W, 0, st>>>(a);
     count_launch();
     LUMI_CUDA_CHECK(cudaGetLastError());
     return;

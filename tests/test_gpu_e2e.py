@@ -489,9 +489,13 @@ def test_lumi_eval_on_the_engine_matches_the_oracle_pipeline(tmp_path):
     want = E.summarize_metrics(ap, ar)
     assert m['total_evaluated'] == 5
     # (the mean over 20 classes is diluted by the classes that never appear; the classes that do must score)
-    assert ap[:, 0].max() > 0.5 and want['AP@0.50'] > 0.0, 'the comparison must not be vacuous'
+    assert np.nanmax(ap[:, 0]) > 0.5, 'the comparison must not be vacuous'
+    # per class, like the reference: a class with detections but no ground truth has recall x / 0 = NaN (eval.py:603),
+    # so the class means can be NaN on a 5-image split -- on both sides alike
+    ap_e = np.array(res[0]['ap_at_50_per_class'])
+    np.testing.assert_allclose(ap_e, ap[:, 0], atol=2e-3, equal_nan=True)
     for k in want:
-        assert abs(m[k] - want[k]) <= 2e-3, (k, m[k], want[k])
+        assert (np.isnan(m[k]) and np.isnan(want[k])) or abs(m[k] - want[k]) <= 2e-3, (k, m[k], want[k])
     assert any('Average Precision (AP) @ [0.50]' in l for l in logs)
 
 
