@@ -136,7 +136,7 @@ struct lumi_engine {
   };
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int launches = 0; int seen = 0; };
   std::map<GraphKey, GraphEntry> graphs;
-  int use_graphs = 0;           // lumi_set_graphs / env LUMI_GRAPHS; off while profiling or tapping
+  int use_graphs = 1;           // lumi_set_graphs / env LUMI_GRAPHS; off while profiling or tapping
   int graph_replays = 0;        // forwards served by a graph replay in the last lumi_predict
   void drop_graphs() {
     for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
