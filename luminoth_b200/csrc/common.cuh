@@ -64,6 +64,15 @@ __device__ __forceinline__ float sub_f32_f16(float x, __half h) {
   asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(__half_as_ushort(h)), "h"((unsigned short)0xBC00), "f"(x));
   return d;
 }
+// x + (hi + lo) in two mixed-precision FMAs (the 2^-11-times-smaller lo plane first): replaces two conversions and
+// two adds of `x + join_f16(hi, lo)` in the conv epilogue's residual add; differs from it by at most one rounding
+// of the partial sum (|lo| <= ulp16(hi) / 2, so x + lo is exact or within 1/2 ulp of x).
+__device__ __forceinline__ float add_f16_pair(float x, __half hi, __half lo) {
+  float t, d;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(t) : "h"(__half_as_ushort(lo)), "h"((unsigned short)0x3C00), "f"(x));
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(__half_as_ushort(hi)), "h"((unsigned short)0x3C00), "f"(t));
+  return d;
+}
 // two values per cvt.rn.f16x2.f32: hi = rn16(v), lo = rn16(v - hi)   (same results as split_f32)
 __device__ __forceinline__ void split2_f32(float a, float b, __half2& hi, __half2& lo) {
   hi = __floats2half2_rn(a, b);

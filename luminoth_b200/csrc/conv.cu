@@ -495,6 +495,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
 #pragma unroll
       for (int j = 0; j < HC; ++j) racc[j] = 0.f;
       for (int rel = 0; rel < n_rel; ++gchunk) {
+        const bool first_chunk = rel == 0;               // its sums initialise the registers (no 0 + x adds)
         rel = tc_chunk_end(rel, n_rel, a.chunk_head, a.chunk_tail);
         const bool last_chunk = rel >= n_rel;
         const uint32_t buf = gchunk & 1u;
@@ -506,8 +507,13 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(lane_base + (uint32_t)(buf * BN + half * HC + ch * 32), r);
             tmem_ld_wait();
+            if (first_chunk) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) racc[ch * 32 + j] = __fadd_rn(racc[ch * 32 + j], __uint_as_float(r[j]));
+              for (int j = 0; j < 32; ++j) racc[ch * 32 + j] = __uint_as_float(r[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) racc[ch * 32 + j] = __fadd_rn(racc[ch * 32 + j], __uint_as_float(r[j]));
+            }
           }
         }
         if (last_chunk) {                                // the last commit also covers every D2 MMA of the tile
@@ -603,7 +609,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
               const __half* ph = reinterpret_cast<const __half*>(&h4);
               const __half* pl = reinterpret_cast<const __half*>(&l4);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[g * 8 + j] += join_f16(ph[j], pl[j]);
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] = add_f16_pair(v[g * 8 + j], ph[j], pl[j]);
             }
             if (!INPLACE) {            // (in place the slab is released by the store leader once the store has read it)
               __syncwarp();            // this warp is done with the slab
@@ -618,7 +624,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
               const __half* ph = reinterpret_cast<const __half*>(&h4);
               const __half* pl = reinterpret_cast<const __half*>(&l4);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[g * 8 + j] += join_f16(ph[j], pl[j]);
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] = add_f16_pair(v[g * 8 + j], ph[j], pl[j]);
             }
           }
 #pragma unroll

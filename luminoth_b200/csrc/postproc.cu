@@ -651,8 +651,12 @@ static void run_nms(NmsWorkspace& ws, int problems, float thr, int max_out, cuda
   if (!problems) return;
   const size_t staged_smem = ((size_t)ws.words + 2 * 64 * (size_t)ws.words) * sizeof(unsigned long long);
   const bool staged = staged_smem <= 200 * 1024;
-  static const bool lazy_on = [] { const char* e = getenv("LUMI_NMS_LAZY"); return e && atoi(e) != 0; }();   // opt-in until validated
-  const bool lazy = lazy_on && staged && ws.sboxes2 && ws.ncap >= NMS_LAZY_MIN && thr > 0.f && thr < INFINITY;
+  // two-phase when the mask kernel is a full-GPU kernel (several long lists at once): measured (call C,
+  // profiles/r2_nms_variants.txt) 0.93 -> 0.75 ms per step at batch 8, but its longer kernel chain costs +0.1 ms of
+  // latency when one or two images are in flight.  LUMI_NMS_LAZY=0 / 1 forces it off / on.
+  static const int lazy_env = [] { const char* e = getenv("LUMI_NMS_LAZY"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+  const bool lazy_ok = staged && ws.sboxes2 && ws.ncap >= NMS_LAZY_MIN && thr > 0.f && thr < INFINITY;
+  const bool lazy = lazy_ok && (lazy_env == 1 || (lazy_env < 0 && problems >= 3));
   if (lazy) {
     const int R1 = NMS_LAZY_R1;
     nms_mask_kernel<<<mask_grid(ws, problems, R1), 64, 0, st>>>(ws.sboxes, ws.nvalid, ws.ncap, ws.words, thr, ws.mask, R1);

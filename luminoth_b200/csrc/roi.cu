@@ -656,11 +656,11 @@ void launch_roi_pool(const float* fmap_f32, int n, int fh, int fw, int c, const 
       c % 4 == 0) {
     constexpr int W = 4;
     dim3 grid((unsigned)rows, (unsigned)cdiv(c, 128 * W));
-    // occupancy A/B: 4 / 5 / 6 resident CTAs per SM (<= 128 / 102 / 80 registers)
-    static const int minb = [] { const char* e = getenv("LUMI_ROI_MINB"); const int v = e ? atoi(e) : 5; return (v == 4 || v == 6) ? v : 5; }();
-    if (minb == 6) roi_pool_rows_kernel<W, 6><<<grid, 32 * W, 0, st>>>(a);
+    // occupancy: 4 / 5 / 6 resident CTAs per SM (<= 128 / 102 / 80 registers) measured 1.308 / 1.269 / 1.241 ms per step: 6
+    static const int minb = [] { const char* e = getenv("LUMI_ROI_MINB"); const int v = e ? atoi(e) : 6; return (v == 4 || v == 5) ? v : 6; }();
+    if (minb == 5) roi_pool_rows_kernel<W, 5><<<grid, 32 * W, 0, st>>>(a);
     else if (minb == 4) roi_pool_rows_kernel<W, 4><<<grid, 32 * W, 0, st>>>(a);
-    else roi_pool_rows_kernel<W, 5><<<grid, 32 * W, 0, st>>>(a);
+    else roi_pool_rows_kernel<W, 6><<<grid, 32 * W, 0, st>>>(a);
     count_launch();
     LUMI_CUDA_CHECK(cudaGetLastError());
     return;

@@ -53,13 +53,19 @@ def frcnn_cfg(arch, extra=()):
                                          'model.rcnn.proposals.min_prob_threshold=0.05'] + list(extra))
 
 
-# Acceptance bound for float outputs.  The north star asks for 1e-3 on box coordinates vs the
-# reference's fp32 CPU path.  Two correct fp32 implementations of this 50-100 layer network already
-# differ by ~6e-4 px on a 224x320 image (fp32 oracle vs the same oracle in fp64, measured; it grows
-# with box size), so the engine is held to: deviation from the exact-arithmetic (fp64) result
-# <= max(1e-3 px, 3 x the fp32 oracle's own deviation from it), identical class assignment.
+# Acceptance bound for float outputs.  The north star asks for 1e-3 px on box coordinates vs the reference's fp32
+# CPU path.  Two fp32 evaluations of this 50-100 layer network differ by their accumulated rounding noise; the fp32
+# oracle's own distance to the float64 evaluation of the same algorithm ("the noise") is 5e-4..1.2e-3 px on a 224x320
+# image and ~1e-2 px in the NMS-stress configuration (it grows with box size).  Measured across every BASELINE
+# configuration (profiles/r2_parity_report_*.json) the engine's distance to float64 is 0.65-1.3 x that noise
+# (round 1: 1.5-2.1 x; the D1 chunk schedule of round 2 closed most of the gap -- DESIGN.md section 3).  The engine
+# is held to max(floor, 1.5 x noise): the floor is the north star's own number, the 1.5 is the measured spread of
+# "one more fp32-class implementation" with margin -- it was 3 in round 1.
+NOISE_FACTOR = 1.5
+
+
 def float_bound(oracle32_dev, floor):
-    return max(floor, 3.0 * oracle32_dev)
+    return max(floor, NOISE_FACTOR * oracle32_dev)
 
 
 @pytest.mark.parametrize('arch,impl', [('resnet_v1_50', 'simt'), ('resnet_v1_50', 'tc'), ('resnet_v1_101', 'tc')])
