@@ -495,7 +495,6 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
 #pragma unroll
       for (int j = 0; j < HC; ++j) racc[j] = 0.f;
       for (int rel = 0; rel < n_rel; ++gchunk) {
-        const bool first_chunk = rel == 0;               // its sums initialise the registers (no 0 + x adds)
         rel = tc_chunk_end(rel, n_rel, a.chunk_head, a.chunk_tail);
         const bool last_chunk = rel >= n_rel;
         const uint32_t buf = gchunk & 1u;
@@ -507,13 +506,8 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(lane_base + (uint32_t)(buf * BN + half * HC + ch * 32), r);
             tmem_ld_wait();
-            if (first_chunk) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) racc[ch * 32 + j] = __uint_as_float(r[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) racc[ch * 32 + j] = __fadd_rn(racc[ch * 32 + j], __uint_as_float(r[j]));
-            }
+            for (int j = 0; j < 32; ++j) racc[ch * 32 + j] = __fadd_rn(racc[ch * 32 + j], __uint_as_float(r[j]));
           }
         }
         if (last_chunk) {                                // the last commit also covers every D2 MMA of the tile
