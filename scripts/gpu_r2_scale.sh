@@ -9,7 +9,9 @@ timeout -s KILL 300 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu-base
 echo "bench n1 exit $?" >> gpurun_out/s_summary.txt
 for n in 2 4 8; do
   NCCL_DEBUG=INFO NCCL_DEBUG_FILE=gpurun_out/s_nccl_n${n}_%h_%p.log timeout -s KILL 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2950$n bench.py --gpus $n --steps 20 --warmup 3 > gpurun_out/s_bench_n$n.json 2> gpurun_out/s_bench_n$n.err
-  echo "bench n$n exit $?" >> gpurun_out/s_summary.txt
+  rc=$?
+  echo "bench n$n exit $rc" >> gpurun_out/s_summary.txt
+  if [ $rc -ne 0 ]; then echo "N=$n failed: stopping the multi-rank runs" >> gpurun_out/s_summary.txt; tail -20 gpurun_out/s_bench_n$n.err; break; fi
 done
 timeout -s KILL 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus 8 --steps 1 --warmup 0 > gpurun_out/s_bench_ref_n8.json 2> gpurun_out/s_bench_ref_n8.err
 echo "bench ref n8 exit $?" >> gpurun_out/s_summary.txt
