@@ -227,13 +227,15 @@ struct TcArgs {
 // One unit of work of a persistent CTA: K iterations [k0, k1) of output tile `tile`.
 struct TcItem { int tile, k0, k1; };
 struct TcSched {
-  int mode, total_tiles, n_iters, t;
+  int mode, total_tiles, n_iters, t, bid, nblk;
   long long u, u_end;
-  __device__ TcSched(int mode_, int total_tiles_, int n_iters_) : mode(mode_), total_tiles(total_tiles_), n_iters(n_iters_) {
-    t = blockIdx.x;
+  // bid / nblk: this CTA's (or CTA pair's) index and the number of them -- blockIdx.x / gridDim.x for single CTAs
+  __device__ TcSched(int mode_, int total_tiles_, int n_iters_, int bid_, int nblk_)
+      : mode(mode_), total_tiles(total_tiles_), n_iters(n_iters_), bid(bid_), nblk(nblk_) {
+    t = bid;
     const long long U = (long long)total_tiles * n_iters;
-    u = U * blockIdx.x / gridDim.x;
-    u_end = U * (blockIdx.x + 1) / gridDim.x;
+    u = U * bid / nblk;
+    u_end = U * (bid + 1) / nblk;
   }
   __device__ static long long range_end(int cta, int total_tiles, int n_iters) {
     return (long long)total_tiles * n_iters * (cta + 1) / gridDim.x;
@@ -242,7 +244,7 @@ struct TcSched {
     if (!mode) {                   // round robin over whole tiles
       if (t >= total_tiles) return false;
       it.tile = t; it.k0 = 0; it.k1 = n_iters;
-      t += gridDim.x;
+      t += nblk;
       return true;
     }
     if (u >= u_end) return false;
@@ -279,11 +281,16 @@ __device__ __forceinline__ int tc_chunk_end(int rel, int n_rel, int head, int ta
   return e < n_rel ? e : n_rel;
 }
 
-template <int BN, int STAGES, bool RES = false, int NSPLIT = 2, bool INPLACE = false>
+// PAIR: two CTAs of a 2-CTA cluster share one 256 x BN tile (tcgen05 cta_group::2): each stages its own 128 rows of A and
+// HALF of the B tile, the leader issues M = 256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM.
+// Operand bytes per CTA and stage drop from 64 KB to 48 KB, which buys a fourth stage: the long-K layers are bound by
+// the operand bytes in flight per SM.
+template <int BN, int STAGES, bool RES = false, int NSPLIT = 2, bool INPLACE = false, bool PAIR = false>
 struct TcCfg {
   static_assert((BN / NSPLIT) % 32 == 0, "each epilogue part owns whole 32-channel slabs");
   static_assert(!INPLACE || (RES && BN / NSPLIT == 32), "in-place residual needs exactly one slab per part");
-  static constexpr int B_BYTES = BN * 128;
+  static_assert(!PAIR || (!RES && BN == 128), "the CTA-pair kernel exists for BN = 128 without residual");
+  static constexpr int B_BYTES = PAIR ? BN * 64 : BN * 128;       // rows of B staged by THIS CTA x 128 B
   static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
   static constexpr int OUT_STAGE_BYTES = NSPLIT * 2 * 128 * 64;   // per column part: hi + lo slabs of 128 rows x 32 ch
   // RES: the whole residual tile (BN/32 slabs x {hi, lo} x 128 rows x 64 B) is TMA-prefetched at tile start
@@ -302,11 +309,16 @@ struct TcCfg {
 // free-running stage / chunk counters, so the producer prefetches the next tile's operands and the
 // tensor core starts the next tile while the epilogue warps are still storing the previous one
 // (D1 and D2 are double-buffered in TMEM).
-template <int BN, int STAGES, bool RES, int NSPLIT, bool INPLACE>
-__global__ void __launch_bounds__(TcCfg<BN, STAGES, RES, NSPLIT, INPLACE>::THREADS, 1)
+template <int BN, int STAGES, bool RES, int NSPLIT, bool INPLACE, bool PAIR>
+__global__ void __launch_bounds__(TcCfg<BN, STAGES, RES, NSPLIT, INPLACE, PAIR>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcArgs a) {
-  using Cfg = TcCfg<BN, STAGES, RES, NSPLIT, INPLACE>;
+  using Cfg = TcCfg<BN, STAGES, RES, NSPLIT, INPLACE, PAIR>;
   constexpr int EPI_WARPS = Cfg::EPI_WARPS;
+  // CTA pair: rank inside the 2-CTA cluster (0 = leader: arms the stage barriers, issues every MMA); scheduling unit =
+  // the pair (sched_id of sched_n); logical tile t = (pair of M tiles, N tile), this CTA's M tile = 2 * pair + rank
+  const int pair_rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment by OFFSET (not by integer round-trip) so the compiler keeps the shared address space
   // and emits LDS/STS for the staging buffers instead of generic LD/ST
@@ -324,13 +336,15 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
-  const int total_tiles = m_tiles * a.n_tiles;
+  const int total_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * a.n_tiles;
   const int rows_valid = a.nb * a.th * a.tw;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&acc_full_bar[s], 1); mbar_init(&acc_empty_bar[s], EPI_WARPS); mbar_init(&d2_empty_bar[s], EPI_WARPS);
+    for (int s = 0; s < 2; ++s) {       // pair: the leader's "drained" barriers collect the epilogue warps of BOTH CTAs
+      mbar_init(&acc_full_bar[s], 1);
+      mbar_init(&acc_empty_bar[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
+      mbar_init(&d2_empty_bar[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
     }
     // res_empty: the slab's four epilogue warps (separate residual staging) or the part's store leader (in place)
     for (int s = 0; s < 4; ++s) { mbar_init(&res_full_bar[s], 1); mbar_init(&res_empty_bar[s], INPLACE ? 1 : 4); }
@@ -342,7 +356,11 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
     if (!a.out_f32) { tma_prefetch_desc(&a.tm_o_hi); tma_prefetch_desc(&a.tm_o_lo); }
     if (RES) { tma_prefetch_desc(&a.tm_r_hi); tma_prefetch_desc(&a.tm_r_lo); }
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (PAIR) cluster_sync_all();          // both CTAs' barriers exist before anything is signalled across the pair
+  if (warp == 1) {
+    if (PAIR) { tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -356,11 +374,11 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
       // ---------------- TMA producer: one (tap, 64-channel) slice per stage
       const uint32_t stage_tx = 2u * (uint32_t)rows_valid * 128u + 2u * (uint32_t)Cfg::B_BYTES;
       uint32_t git = 0;
-      TcSched sched(a.sk_mode, total_tiles, n_iters);
+      TcSched sched(a.sk_mode, total_tiles, n_iters, sched_id, sched_n);
       TcItem item;
       while (sched.next(item)) {
         const int t = a.reverse ? total_tiles - 1 - item.tile : item.tile;
-        const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+        const int nt = t % a.n_tiles, mt = PAIR ? 2 * (t / a.n_tiles) + pair_rank : t / a.n_tiles;
         const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
         const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
         for (int k = item.k0; k < item.k1; ++k, ++git) {
@@ -370,21 +388,32 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           const uint32_t st = git % STAGES, ph = (git / STAGES) & 1u;
           mbar_wait(&empty_bar[st], ph ^ 1u);
           uint8_t* sbase = smem + st * Cfg::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[st], stage_tx);
-          tma_load_4d(sbase, &a.tm_a_hi, &full_bar[st], cc * 64, ix, iy, img0);
-          tma_load_4d(sbase + TC_A_BYTES, &a.tm_a_lo, &full_bar[st], cc * 64, ix, iy, img0);
           const int kcol = tap * a.cin + cc * 64;
-          tma_load_2d(sbase + 2 * TC_A_BYTES, &a.tm_b_hi, &full_bar[st], kcol, n0);
-          tma_load_2d(sbase + 2 * TC_A_BYTES + Cfg::B_BYTES, &a.tm_b_lo, &full_bar[st], kcol, n0);
+          if (PAIR) {
+            // the leader arms its barrier for the bytes of BOTH CTAs; either CTA's loads complete on that barrier
+            // (a tile of the odd CTA past the last M tile lies outside the tensor: zero-filled, same byte count)
+            if (pair_rank == 0) mbar_arrive_expect_tx(&full_bar[st], 2u * stage_tx);
+            tma_load_4d_2sm(sbase, &a.tm_a_hi, &full_bar[st], cc * 64, ix, iy, img0);
+            tma_load_4d_2sm(sbase + TC_A_BYTES, &a.tm_a_lo, &full_bar[st], cc * 64, ix, iy, img0);
+            tma_load_2d_2sm(sbase + 2 * TC_A_BYTES, &a.tm_b_hi, &full_bar[st], kcol, n0 + pair_rank * (BN / 2));
+            tma_load_2d_2sm(sbase + 2 * TC_A_BYTES + Cfg::B_BYTES, &a.tm_b_lo, &full_bar[st], kcol, n0 + pair_rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[st], stage_tx);
+            tma_load_4d(sbase, &a.tm_a_hi, &full_bar[st], cc * 64, ix, iy, img0);
+            tma_load_4d(sbase + TC_A_BYTES, &a.tm_a_lo, &full_bar[st], cc * 64, ix, iy, img0);
+            tma_load_2d(sbase + 2 * TC_A_BYTES, &a.tm_b_hi, &full_bar[st], kcol, n0);
+            tma_load_2d(sbase + 2 * TC_A_BYTES + Cfg::B_BYTES, &a.tm_b_lo, &full_bar[st], kcol, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && pair_rank == 0) {
       // ---------------- MMA issuer: per K=16 slice  D1 += Ahi*Bhi ;  D2 += Ahi*Blo + Alo*Bhi
-      constexpr uint32_t idesc = make_idesc_f16(128, BN);
+      // (pair: only the leader issues; M = 256 spans both CTAs' A rows and accumulators)
+      constexpr uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, BN);
       uint32_t git = 0, gchunk = 0, tile_iter = 0;
-      TcSched sched(a.sk_mode, total_tiles, n_iters);
+      TcSched sched(a.sk_mode, total_tiles, n_iters, sched_id, sched_n);
       TcItem item;
       for (; sched.next(item); ++tile_iter) {
         const uint32_t tbuf = tile_iter & 1u;
@@ -416,13 +445,21 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ko = (uint64_t)(k * 2);      // 16 fp16 = 32 B = 2 x 16 B units
-            umma_f16(d1, d_ahi + ko, d_bhi + ko, idesc, (!first_of_chunk || k > 0) ? 1u : 0u);
-            umma_f16(d2, d_ahi + ko, d_blo + ko, idesc, (it > item.k0 || k > 0) ? 1u : 0u);
-            umma_f16(d2, d_alo + ko, d_bhi + ko, idesc, 1u);
+            if (PAIR) {
+              umma_f16_2sm(d1, d_ahi + ko, d_bhi + ko, idesc, (!first_of_chunk || k > 0) ? 1u : 0u);
+              umma_f16_2sm(d2, d_ahi + ko, d_blo + ko, idesc, (it > item.k0 || k > 0) ? 1u : 0u);
+              umma_f16_2sm(d2, d_alo + ko, d_bhi + ko, idesc, 1u);
+            } else {
+              umma_f16(d1, d_ahi + ko, d_bhi + ko, idesc, (!first_of_chunk || k > 0) ? 1u : 0u);
+              umma_f16(d2, d_ahi + ko, d_blo + ko, idesc, (it > item.k0 || k > 0) ? 1u : 0u);
+              umma_f16(d2, d_alo + ko, d_bhi + ko, idesc, 1u);
+            }
           }
-          umma_commit(&empty_bar[st]);                  // frees the smem slot once these MMAs retire
+          // frees the smem slot once these MMAs retire (pair: in both CTAs)
+          if (PAIR) umma_commit_2sm(&empty_bar[st], 0x3); else umma_commit(&empty_bar[st]);
           if (rel + 1 == chunk_stop) {
-            umma_commit(&acc_full_bar[buf]);            // D1[buf] (and, on the last chunk, D2[tbuf]) complete
+            // D1[buf] (and, on the last chunk, D2[tbuf]) complete -- published to the epilogue warps of both CTAs
+            if (PAIR) umma_commit_2sm(&acc_full_bar[buf], 0x3); else umma_commit(&acc_full_bar[buf]);
             ++gchunk;
           }
         }
@@ -435,7 +472,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
       // It runs on its own warp so that it never holds back the operand loads of the next tile.
       const uint32_t slab_tx = 2u * (uint32_t)rows_valid * 64u;
       uint32_t tile_iter = 0;                       // counts the tiles whose epilogue runs in this CTA
-      TcSched sched(a.sk_mode, total_tiles, n_iters);
+      TcSched sched(a.sk_mode, total_tiles, n_iters, sched_id, sched_n);
       TcItem item;
       while (sched.next(item)) {
         if (item.k0 != 0) continue;                 // partial contribution: no epilogue here
@@ -467,12 +504,12 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t gchunk = 0, tile_iter = 0, epi_iter = 0;
-    TcSched sched(a.sk_mode, total_tiles, n_iters);
+    TcSched sched(a.sk_mode, total_tiles, n_iters, sched_id, sched_n);
     TcItem item;
     for (; sched.next(item); ++tile_iter) {
       const int t = a.reverse ? total_tiles - 1 - item.tile : item.tile;    // coordinates only: the schedule is unchanged
       const int n_rel = item.k1 - item.k0;
-      const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+      const int nt = t % a.n_tiles, mt = PAIR ? 2 * (t / a.n_tiles) + pair_rank : t / a.n_tiles;
       const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
       const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb;
       const int n0 = nt * BN + half * HC;               // first channel of this warp's columns
@@ -523,11 +560,11 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&d2_empty_bar[tbuf]);
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(&d2_empty_bar[tbuf]); else mbar_arrive(&d2_empty_bar[tbuf]); }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(&acc_empty_bar[buf]); else mbar_arrive(&acc_empty_bar[buf]); }
       }
 
       // ---- stream-K fix-up
@@ -664,8 +701,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
             fence_proxy_async();
             named_bar_sync(1 + half, 128);
             if (store_leader) {
-              tma_store_4d(&a.tm_o_hi, st_hi, c0, x0, y0, img0);
-              tma_store_4d(&a.tm_o_lo, st_lo, c0, x0, y0, img0);
+              if (!PAIR || mt < m_tiles) {       // (the odd CTA's tile past the last M tile has nothing to store)
+                tma_store_4d(&a.tm_o_hi, st_hi, c0, x0, y0, img0);
+                tma_store_4d(&a.tm_o_lo, st_lo, c0, x0, y0, img0);
+              }
               bulk_commit_group();
               if (INPLACE) {           // hand the slab back to the residual producer once the store has read it
                 bulk_wait_group_read0();
@@ -681,9 +720,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();          // the peer's shared memory / TMEM / barriers stay alive until both CTAs are done
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -860,23 +900,42 @@ void conv_workspace_free(ConvWorkspace& w) {
   w.partials = nullptr; w.flags = nullptr; w.ctas = 0;
 }
 
-template <int BN, int STAGES, bool RES, int NSPLIT = 2, bool INPLACE = false>
+template <int BN, int STAGES, bool RES, int NSPLIT = 2, bool INPLACE = false, bool PAIR = false>
 static void launch_tc_cfg(const TcArgs& a, ConvWorkspace* sk, int streamk, int sm_reserve, cudaStream_t st) {
-  using Cfg = TcCfg<BN, STAGES, RES, NSPLIT, INPLACE>;
+  using Cfg = TcCfg<BN, STAGES, RES, NSPLIT, INPLACE, PAIR>;
   // cudaFuncSetAttribute is per device: one flag per (kernel instance, device)
   static bool attr_set[LUMI_MAX_DEVICES] = {false};
   int dev = 0;
   LUMI_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= LUMI_MAX_DEVICES || !__atomic_load_n(&attr_set[dev], __ATOMIC_ACQUIRE)) {
-    LUMI_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE>,
+    LUMI_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE, PAIR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (dev >= 0 && dev < LUMI_MAX_DEVICES) __atomic_store_n(&attr_set[dev], true, __ATOMIC_RELEASE);
   }
-  const long total = (long)a.tiles_w * a.tiles_h * a.tiles_n * a.n_tiles;
+  const long m_tiles = (long)a.tiles_w * a.tiles_h * a.tiles_n;
+  const long total = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * a.n_tiles;      // scheduling units (tiles or tile pairs)
   const int sms = sm_budget(sm_reserve);
-  int grid = (int)(total < sms ? total : sms);                          // persistent: one CTA per SM
   TcArgs args = a;
   args.sk_mode = 0;
+  if (PAIR) {
+    // persistent 2-CTA clusters: one pair per unit, at most sms / 2 pairs; whole-tile schedule only
+    const int pairs = (int)std::min<long>(total, sms / 2);
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    LUMI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE, PAIR>, args));
+    count_launch();
+    return;
+  }
+  int grid = (int)(total < sms ? total : sms);                          // persistent: one CTA per SM
   if (sk && sk->partials && streamk > 0 && sms <= sk->ctas) {
     // stream-K when whole-tile scheduling would leave SMs idle in the last wave (or has fewer tiles than SMs).
     // It balances K iterations, not epilogues, and every CTA pays one partial-tile write and one read: measured
@@ -895,7 +954,7 @@ static void launch_tc_cfg(const TcArgs& a, ConvWorkspace* sk, int streamk, int s
       grid = sms;
     }
   }
-  conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(args);
+  conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE, PAIR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(args);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
@@ -934,6 +993,14 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   a.chunk_tail = (io.chunk_tail >= 1 && io.chunk_tail <= TC_CHUNK_STAGES) ? io.chunk_tail : TC_CHUNK_STAGES;
   a.overflow = io.overflow_flag;
   const bool res_tma = io.res.hi != nullptr && bn == 128 && L.cout % 128 == 0 && !io.out_f32;
+  // CTA pairs (cta_group::2) for the long-K layers without residual: 48 KB of operands per CTA and stage, four stages
+  const long n_iters_all = (long)L.kh * L.kw * (L.cin >> 6);
+  if (io.cta2 && bn == 128 && !io.res.hi && !io.out_f32 && n_iters_all >= io.cta2) {
+    a.tm_b_hi = cached_wgt_map(L.w_hi, L.cout_pad, kdim, 64);       // each CTA of a pair loads 64 of the 128 B rows
+    a.tm_b_lo = cached_wgt_map(L.w_lo, L.cout_pad, kdim, 64);
+    launch_tc_cfg<128, 4, false, 2, false, true>(a, io.sk, io.streamk, io.sm_reserve, st);
+    return;
+  }
   // 16 epilogue warps for the shortest-K layers (io.epi16 = largest K-stage count that uses them; measured per layer,
   // profiles/r2_conv_variants.txt: they win on one-stage tiles (C_in = 64) and lose from four stages up, where their
   // two operand stages cost more than the faster epilogue gains)

@@ -117,6 +117,7 @@ struct lumi_engine {
   ConvWorkspace sk_ws[2];       // stream-K scratch, one per stream
   int conv_streamk = 1;         // 0 off, 1 auto, 2 whenever possible
   int conv_chunk_tail = 2;      // env LUMI_CONV_CHUNK_TAIL: D1 chunk length (stages) past the first eight stages of a tile
+  int conv_cta2 = 0;            // env LUMI_CONV_2CTA: minimum K stages per tile for the CTA-pair kernel (0 = off)
   int conv_epi16 = 1;           // env LUMI_CONV_EPI16: 16-epilogue-warp kernels for tiles of at most this many K stages
   int conv_serpentine = 0;      // env LUMI_CONV_SERPENTINE: consecutive conv layers walk their tiles in opposite directions
   uint8_t* d_images = nullptr; size_t images_cap = 0;
@@ -653,6 +654,7 @@ Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* re
   io.streamk = cx.e->conv_streamk;
   io.sm_reserve = cx.sm_reserve;
   io.epi16 = cx.e->conv_epi16;
+  io.cta2 = cx.e->conv_cta2;
   io.chunk_tail = cx.e->conv_chunk_tail;
   if (cx.e->conv_serpentine) { io.reverse = cx.conv_parity; cx.conv_parity ^= 1; }
   if (!cx.dry) {
@@ -1163,6 +1165,7 @@ int lumi_finalize(lumi_engine* e) {
   if (const char* v = std::getenv("LUMI_GRAPHS")) e->use_graphs = std::atoi(v) != 0;
   if (const char* v = std::getenv("LUMI_CONV_SERPENTINE")) e->conv_serpentine = std::atoi(v) != 0;
   if (const char* v = std::getenv("LUMI_CONV_EPI16")) e->conv_epi16 = std::max(0, std::min(8, std::atoi(v)));
+  if (const char* v = std::getenv("LUMI_CONV_2CTA")) e->conv_cta2 = std::max(0, std::atoi(v));
   if (const char* v = std::getenv("LUMI_CONV_CHUNK_TAIL")) e->conv_chunk_tail = std::max(1, std::min(4, std::atoi(v)));
   if (e->max_batch >= 2) {
     conv_workspace_create(e->sk_ws[1]);
