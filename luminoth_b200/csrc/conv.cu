@@ -237,8 +237,8 @@ struct TcSched {
     u = U * bid / nblk;
     u_end = U * (bid + 1) / nblk;
   }
-  __device__ static long long range_end(int cta, int total_tiles, int n_iters) {
-    return (long long)total_tiles * n_iters * (cta + 1) / gridDim.x;
+  __device__ static long long range_end(int unit, int total_tiles, int n_iters, int nblk_) {
+    return (long long)total_tiles * n_iters * (unit + 1) / nblk_;
   }
   __device__ bool next(TcItem& it) {
     if (!mode) {                   // round robin over whole tiles
@@ -583,8 +583,11 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
       if (item.k1 != n_iters) {
         // this CTA holds the head of the tile: the following CTAs hold the rest (they computed it first thing)
         const long long tile_end = (long long)(item.tile + 1) * n_iters;
-        int last = blockIdx.x;
-        for (int cta = blockIdx.x + 1;; ++cta) {
+        // scheduling units after this one hold the rest of the tile; in a CTA pair every unit is a pair and this CTA's
+        // partner in unit u is the CTA of the same rank: its partial slot / flag index is 2 u + rank
+        int last_unit = sched_id;
+        for (int unit = sched_id + 1;; ++unit) {
+          const int cta = PAIR ? 2 * unit + pair_rank : unit;
           int seen;
           do {
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(a.sk_flags + cta) : "memory");
@@ -592,15 +595,15 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           const float* wsp = a.sk_partials + (size_t)cta * (128 * BN) + (size_t)(half * HC) * 128 + row;
 #pragma unroll
           for (int j = 0; j < HC; ++j) racc[j] = __fadd_rn(racc[j], __ldcg(wsp + j * 128));
-          last = cta;
-          if (TcSched::range_end(cta, total_tiles, n_iters) >= tile_end) break;
+          last_unit = unit;
+          if (TcSched::range_end(unit, total_tiles, n_iters, sched_n) >= tile_end) break;
         }
         // every flag is consumed by exactly one CTA (the one holding the tile's head): clear it once all
         // epilogue warps are past their polls, so a REPLAY of this launch with the same epoch (CUDA graph) starts clean
         named_bar_sync(7, 32 * EPI_WARPS);
         if (warp == 2 && lane == 0)
-          for (int cta = blockIdx.x + 1; cta <= last; ++cta)
-            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(a.sk_flags + cta), "r"(0) : "memory");
+          for (int unit = sched_id + 1; unit <= last_unit; ++unit)
+            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(a.sk_flags + (PAIR ? 2 * unit + pair_rank : unit)), "r"(0) : "memory");
       }
 
       // ---- scale/bias (folded BN) -> +residual -> activation -> store (overlaps the next tile's MMAs)
@@ -917,12 +920,31 @@ static void launch_tc_cfg(const TcArgs& a, ConvWorkspace* sk, int streamk, int s
   const int sms = sm_budget(sm_reserve);
   TcArgs args = a;
   args.sk_mode = 0;
+  // scheduling units: CTAs, or 2-CTA clusters for the pair kernel
+  const int units_max = PAIR ? sms / 2 : sms;
+  int units = (int)(total < units_max ? total : units_max);             // persistent: one CTA (pair) per SM (pair)
+  if (sk && sk->partials && streamk > 0 && sms <= sk->ctas) {
+    // stream-K when whole-tile scheduling would leave SMs idle in the last wave (or has fewer tiles than SMs).
+    // It balances K iterations, not epilogues, and every CTA pays one partial-tile write and one read: measured
+    // (profiles/r1_streamk_per_layer.txt) it wins 13-26 % on the long-K layers (3x3 with C_in >= 128,
+    // 1x1 with C_in >= 1024, the RPN conv) and loses 5-35 % on short-K, epilogue-bound ones -- hence the K floor.
+    const long n_iters = (long)a.kh * a.kw * (a.cin >> 6);
+    const double waves = (double)total / units_max;
+    const double eff = waves / std::ceil(waves);
+    const long units_per_cta = total * n_iters / units_max;
+    const bool forced = streamk >= 2 && units_per_cta >= 3;
+    if (forced || (eff < 0.92 && n_iters >= 12 && units_per_cta >= 12)) {
+      args.sk_mode = 1;
+      args.sk_partials = sk->partials;
+      args.sk_flags = sk->flags;
+      args.sk_epoch = (int)(++sk->epoch & 0x7fffffff);
+      units = units_max;
+    }
+  }
   if (PAIR) {
-    // persistent 2-CTA clusters: one pair per unit, at most sms / 2 pairs; whole-tile schedule only
-    const int pairs = (int)std::min<long>(total, sms / 2);
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.gridDim = dim3(2 * units, 1, 1);
     cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
@@ -935,25 +957,7 @@ static void launch_tc_cfg(const TcArgs& a, ConvWorkspace* sk, int streamk, int s
     count_launch();
     return;
   }
-  int grid = (int)(total < sms ? total : sms);                          // persistent: one CTA per SM
-  if (sk && sk->partials && streamk > 0 && sms <= sk->ctas) {
-    // stream-K when whole-tile scheduling would leave SMs idle in the last wave (or has fewer tiles than SMs).
-    // It balances K iterations, not epilogues, and every CTA pays one partial-tile write and one read: measured
-    // (profiles/r1_streamk_per_layer.txt) it wins 13-26 % on the long-K layers (3x3 with C_in >= 128,
-    // 1x1 with C_in >= 1024, the RPN conv) and loses 5-35 % on short-K, epilogue-bound ones -- hence the K floor.
-    const long n_iters = (long)a.kh * a.kw * (a.cin >> 6);
-    const double waves = (double)total / sms;
-    const double eff = waves / std::ceil(waves);
-    const long units_per_cta = total * n_iters / sms;
-    const bool forced = streamk >= 2 && units_per_cta >= 3;
-    if (forced || (eff < 0.92 && n_iters >= 12 && units_per_cta >= 12)) {
-      args.sk_mode = 1;
-      args.sk_partials = sk->partials;
-      args.sk_flags = sk->flags;
-      args.sk_epoch = (int)(++sk->epoch & 0x7fffffff);
-      grid = sms;
-    }
-  }
+  const int grid = units;
   conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE, PAIR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(args);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());

@@ -81,7 +81,7 @@ int lumi_op_conv2d(const float* x, int n, int h, int w, int cin, const float* wg
     launch_f32_to_act(residual, res->a, st);
     io.res = res->a; io.res_stride = 1;
   }
-  if (impl >= 1 && impl <= 6) {
+  if (impl >= 1 && impl <= 7) {
     // 1 whole tiles, 2 stream-K forced (fp32 outputs written by the epilogue);
     // 3 / 4 / 5: the engine's inter-layer form -- fp16x2 split planes through the staged TMA-store epilogue (and the
     // TMA-prefetched residual) -- with the 8-warp epilogue (3), the 16-warp short-K kernels allowed (4), and 4 + stream-K (5)
@@ -92,12 +92,12 @@ int lumi_op_conv2d(const float* x, int n, int h, int w, int cin, const float* wg
       io.out = split_out->a;
       io.out_f32 = nullptr;
       io.epi16 = (impl == 4 || impl == 5) ? 8 : 0;
-      io.cta2 = impl == 6 ? 1 : 0;          // 6: CTA-pair kernel wherever it applies
+      io.cta2 = (impl == 6 || impl == 7) ? 1 : 0;   // 6 / 7: CTA-pair kernel wherever it applies (7: + stream-K forced)
     }
     LUMI_REQUIRE(conv_tc_supported(L, io), "conv2d: this layer shape is not handled by the tensor-core kernel");
     ConvWorkspace sk;
     struct SkGuard { ConvWorkspace& w; ~SkGuard() { conv_workspace_free(w); } } skg{sk};
-    if (impl == 2 || impl == 5) {
+    if (impl == 2 || impl == 5 || impl == 7) {
       conv_workspace_create(sk);
       io.sk = &sk;
       io.streamk = 2;

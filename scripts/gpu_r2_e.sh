@@ -5,7 +5,7 @@ timeout -s KILL 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:c
 echo "pytest cta2 exit $?" > gpurun_out/e_summary.txt
 tail -n 30 gpurun_out/e_pytest_cta2.log
 if grep -q " passed" gpurun_out/e_pytest_cta2.log && ! grep -q "failed" gpurun_out/e_pytest_cta2.log; then
-  for m in 9 16; do
+  for m in 9 36; do
     LUMI_CONV_2CTA=$m timeout -s KILL 300 python bench.py --steps 20 --warmup 4 --layers --no-cpu-baseline > gpurun_out/e_bench_r50_cta2_$m.json 2> gpurun_out/e_bench_r50_cta2_$m.err
     echo "bench cta2 $m exit $?" >> gpurun_out/e_summary.txt
   done
@@ -18,7 +18,7 @@ fi
 cat gpurun_out/e_summary.txt
 python - <<'PY'
 import json
-for wl in ('r50_base','r50_cta2_9','r50_cta2_16','ssd_cta2','r101_cta2'):
+for wl in ('r50_base','r50_cta2_9','r50_cta2_36','ssd_cta2','r101_cta2'):
     try:
         d=json.load(open('gpurun_out/e_bench_%s.json'%wl)); print(wl, round(d['value'],1), round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['category_ms_per_step'].items() if v>0}, round(d['roofline']['frac'],4))
     except Exception as e: print(wl, 'ERR', e)

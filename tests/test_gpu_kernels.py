@@ -76,7 +76,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc_streamk', 'tc_split', 'tc_split_epi16', 'tc_split_epi16_streamk', 'tc_split_cta2'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc_streamk', 'tc_split', 'tc_split_epi16', 'tc_split_epi16_streamk', 'tc_split_cta2', 'tc_split_cta2_streamk'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv2d_matches_oracle(case, impl):
     name, n, h, w, cin, cout, k, stride, rate, padding, use_res, act = case
