@@ -117,7 +117,8 @@ struct lumi_engine {
   ConvWorkspace sk_ws[2];       // stream-K scratch, one per stream
   int conv_streamk = 1;         // 0 off, 1 auto, 2 whenever possible
   int conv_chunk_tail = 2;      // env LUMI_CONV_CHUNK_TAIL: D1 chunk length (stages) past the first eight stages of a tile
-  int conv_cta2 = 0;            // env LUMI_CONV_2CTA: minimum K stages per tile for the CTA-pair kernel (0 = off)
+  int conv_cta2 = 64;           // env LUMI_CONV_2CTA: minimum K stages per tile for the CTA-pair kernel (0 = off); measured:
+                                // wins from ~64 stages (RPN 3x3x1024: 488 -> 460 us, SSD / R101-tail 3x3x512), loses 1-3 % below
   int conv_epi16 = 1;           // env LUMI_CONV_EPI16: 16-epilogue-warp kernels for tiles of at most this many K stages
   int conv_serpentine = 0;      // env LUMI_CONV_SERPENTINE: consecutive conv layers walk their tiles in opposite directions
   uint8_t* d_images = nullptr; size_t images_cap = 0;
