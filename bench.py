@@ -207,8 +207,9 @@ def run_ours(args, wl):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner (printed at NCCL_DEBUG=VERSION *and* WARN) and any
+        # other NCCL log line go to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
