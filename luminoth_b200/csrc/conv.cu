@@ -212,7 +212,6 @@ struct TcArgs {
   int n_tiles;                     // C_out tiles (cout_pad / BN)
   int stride;                      // TMA traversal stride of the activation map (1 or 2)
   int chunk_head, chunk_tail;      // D1 chunk schedule, see tc_chunk_end()
-  int reverse;                     // 1: walk the output tiles last-to-first (serpentine order across consecutive layers)
   int* overflow;
   // stream-K (sk_mode != 0): the K loops of all tiles form one unit sequence that is cut into gridDim.x equal
   // contiguous ranges; a CTA that starts in the middle of a tile writes its partial accumulators to
@@ -377,7 +376,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
       TcSched sched(a.sk_mode, total_tiles, n_iters, sched_id, sched_n);
       TcItem item;
       while (sched.next(item)) {
-        const int t = a.reverse ? total_tiles - 1 - item.tile : item.tile;
+        const int t = item.tile;
         const int nt = t % a.n_tiles, mt = PAIR ? 2 * (t / a.n_tiles) + pair_rank : t / a.n_tiles;
         const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
         const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
@@ -476,7 +475,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
       TcItem item;
       while (sched.next(item)) {
         if (item.k0 != 0) continue;                 // partial contribution: no epilogue here
-        const int t = a.reverse ? total_tiles - 1 - item.tile : item.tile;
+        const int t = item.tile;
         const int nt = t % a.n_tiles, mt = t / a.n_tiles;
         const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
         const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
@@ -507,7 +506,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
     TcSched sched(a.sk_mode, total_tiles, n_iters, sched_id, sched_n);
     TcItem item;
     for (; sched.next(item); ++tile_iter) {
-      const int t = a.reverse ? total_tiles - 1 - item.tile : item.tile;    // coordinates only: the schedule is unchanged
+      const int t = item.tile;
       const int n_rel = item.k1 - item.k0;
       const int nt = t % a.n_tiles, mt = PAIR ? 2 * (t / a.n_tiles) + pair_rank : t / a.n_tiles;
       const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
@@ -992,7 +991,6 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   a.tiles_w = cdiv(io.wo, tw); a.tiles_h = cdiv(io.ho, th); a.tiles_n = cdiv(io.in.n, nb);
   a.n_tiles = L.cout_pad / bn;
   a.stride = L.stride;
-  a.reverse = io.reverse;
   a.chunk_head = 2 * TC_CHUNK_STAGES;
   a.chunk_tail = (io.chunk_tail >= 1 && io.chunk_tail <= TC_CHUNK_STAGES) ? io.chunk_tail : TC_CHUNK_STAGES;
   a.overflow = io.overflow_flag;

@@ -48,8 +48,6 @@ struct ConvIO {
   int* overflow_flag = nullptr;
   ConvWorkspace* sk = nullptr;  // enables stream-K scheduling on the tcgen05 path (nullptr: whole tiles only)
   int streamk = 1;              // stream-K policy of THIS launch: 0 off, 1 auto (wave-quantisation heuristic), 2 whenever possible
-  int reverse = 0;              // walk output tiles last-to-first: with the previous layer walking first-to-last, this
-                                // layer starts on the activations that are still resident in L2 (serpentine order)
   int chunk_tail = 2;           // stages per D1 chunk after the first eight stages of a tile (1, 2 or 4; see tc_chunk_end)
   int cta2 = 0;                 // CTA-pair (cta_group::2) kernel on residual-free layers with at least this many K stages per tile (0 = never)
   int epi16 = 0;                // 16-epilogue-warp kernels on layers with at most this many K stages per tile (0 = never)

@@ -120,7 +120,6 @@ struct lumi_engine {
   int conv_cta2 = 64;           // env LUMI_CONV_2CTA: minimum K stages per tile for the CTA-pair kernel (0 = off); measured:
                                 // wins from ~64 stages (RPN 3x3x1024: 488 -> 460 us, SSD / R101-tail 3x3x512), loses 1-3 % below
   int conv_epi16 = 1;           // env LUMI_CONV_EPI16: 16-epilogue-warp kernels for tiles of at most this many K stages
-  int conv_serpentine = 0;      // env LUMI_CONV_SERPENTINE: consecutive conv layers walk their tiles in opposite directions
   uint8_t* d_images = nullptr; size_t images_cap = 0;
   float* d_boxes = nullptr; float* d_scores = nullptr; int* d_labels = nullptr; int* d_counts = nullptr;
   int* d_prop_counts = nullptr;
@@ -568,7 +567,6 @@ struct Ctx {
   bool taps = true;             // record debug taps (first half only)
   bool img_f32 = false;         // input pixels are float32 (resized images) instead of uint8
   int sm_reserve = 0;           // SMs the persistent conv launches of this forward leave to the other stream
-  int conv_parity = 0;          // alternates per conv launch when the serpentine tile order is on
   Act act(int n, int h, int w, int c) {
     Act a; a.n = n; a.h = h; a.w = w; a.c = c;
     const size_t bytes = a.numel() * sizeof(__half);
@@ -657,7 +655,6 @@ Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* re
   io.epi16 = cx.e->conv_epi16;
   io.cta2 = cx.e->conv_cta2;
   io.chunk_tail = cx.e->conv_chunk_tail;
-  if (cx.e->conv_serpentine) { io.reverse = cx.conv_parity; cx.conv_parity ^= 1; }
   if (!cx.dry) {
     const bool tc = cx.e->conv_impl == 1 && conv_tc_supported(L, io);
     const double flops = algorithmic_flops >= 0 ? algorithmic_flops
@@ -1164,7 +1161,6 @@ int lumi_finalize(lumi_engine* e) {
   conv_workspace_create(e->sk_ws[0]);
   if (const char* v = std::getenv("LUMI_CONV_STREAMK")) e->conv_streamk = std::max(0, std::min(2, std::atoi(v)));
   if (const char* v = std::getenv("LUMI_GRAPHS")) e->use_graphs = std::atoi(v) != 0;
-  if (const char* v = std::getenv("LUMI_CONV_SERPENTINE")) e->conv_serpentine = std::atoi(v) != 0;
   if (const char* v = std::getenv("LUMI_CONV_EPI16")) e->conv_epi16 = std::max(0, std::min(8, std::atoi(v)));
   if (const char* v = std::getenv("LUMI_CONV_2CTA")) e->conv_cta2 = std::max(0, std::atoi(v));
   if (const char* v = std::getenv("LUMI_CONV_CHUNK_TAIL")) e->conv_chunk_tail = std::max(1, std::min(4, std::atoi(v)));
