@@ -68,11 +68,14 @@ def build_library(force=False, verbose=False):
     # defined order at interpreter exit (a second, static runtime needed os._exit in bench.py); the rpath covers
     # processes that load the library without torch.
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), 'lib64')
-    cmd = ([nvcc, '-shared', '-cudart', 'shared', '-o', LIB] + objs +
+    # link into a temporary name and rename: a reader (a gpurun snapshot, another process) never sees a half-written file
+    tmp = LIB + '.tmp.%d' % os.getpid()
+    cmd = ([nvcc, '-shared', '-cudart', 'shared', '-o', tmp] + objs +
            ['-gencode', 'arch=compute_100a,code=sm_100a', '-Xlinker', '-rpath', '-Xlinker', cuda_lib, '-ldl'])
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -267,6 +267,19 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
   return d;
 }
+// The same with an explicit stride between the 8-row groups and a start address that need not sit on a 1024 B
+// boundary (shifted views into a halo patch, conv.cu HALO kernels).  base_off = matrix base offset field [49,52):
+// the phase of the start address inside the 1024 B swizzle pattern ((addr >> 7) & 7) when the hardware expects it there.
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_off & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: A,B = F16 (K-major), D = F32, M x N.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);

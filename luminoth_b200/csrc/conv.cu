@@ -212,6 +212,7 @@ struct TcArgs {
   int n_tiles;                     // C_out tiles (cout_pad / BN)
   int stride;                      // TMA traversal stride of the activation map (1 or 2)
   int chunk_head, chunk_tail;      // D1 chunk schedule, see tc_chunk_end()
+  int halo_baseoff;                // HALO kernels: 1 = write the start address' swizzle phase into the descriptors
   int* overflow;
   // stream-K (sk_mode != 0): the K loops of all tiles form one unit sequence that is cut into gridDim.x equal
   // contiguous ranges; a CTA that starts in the middle of a tile writes its partial accumulators to
@@ -284,18 +285,36 @@ __device__ __forceinline__ int tc_chunk_end(int rel, int n_rel, int head, int ta
 // HALF of the B tile, the leader issues M = 256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM.
 // Operand bytes per CTA and stage drop from 64 KB to 48 KB, which buys a fourth stage: the long-K layers are bound by
 // the operand bytes in flight per SM.
-template <int BN, int STAGES, bool RES = false, int NSPLIT = 2, bool INPLACE = false, bool PAIR = false>
+//
+// HALO (3x3, stride 1, rate 1): the nine taps of a 64-channel slice read the SAME input pixels, shifted.  The generic
+// kernel fetches them nine times from L2 (one im2col box per tap), and the long-K layers are bound by exactly that
+// L2 -> shared-memory operand traffic (64 KB per 12 MMAs; ~6300 B/clk for the whole chip).  The HALO kernels fetch the
+// (th+2) x (8+2)-pixel patch of the slice ONCE (one TMA box per plane, zero-filled outside the image = SAME padding)
+// and hand the tensor core nine shifted VIEWS of it: M tile = th rows x 8 pixels, 8-row group g = image row g, so a
+// view is the K-major SWIZZLE_128B matrix that starts at patch pixel (r, s) with a group stride of one patch row
+// (10 pixels = 1280 B).  Only the weights stream per tap.  A traffic drops ~6x, total operand traffic 1.7x (BN = 128)
+// to 2.3x (BN = 64).
+constexpr int TC_HALO_TW = 8;                              // tile width: one 8-row swizzle group per image row
+constexpr int TC_HALO_PITCH = (TC_HALO_TW + 2) * 128;      // bytes per patch row (10 pixels x 64 fp16)
+constexpr int TC_HALO_PLANE_BYTES = ((16 + 2) * TC_HALO_PITCH + 1023) / 1024 * 1024;   // th <= 16
+
+template <int BN, int STAGES, bool RES = false, int NSPLIT = 2, bool INPLACE = false, bool PAIR = false,
+          bool HALO = false>
 struct TcCfg {
   static_assert((BN / NSPLIT) % 32 == 0, "each epilogue part owns whole 32-channel slabs");
   static_assert(!INPLACE || (RES && BN / NSPLIT == 32), "in-place residual needs exactly one slab per part");
   static_assert(!PAIR || (!RES && BN == 128), "the CTA-pair kernel exists for BN = 128 without residual");
+  static_assert(!HALO || !RES, "the halo kernels have no residual input (conv2 of a bottleneck, RPN conv, VGG)");
   static constexpr int B_BYTES = PAIR ? BN * 64 : BN * 128;       // rows of B staged by THIS CTA x 128 B
-  static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  static constexpr int A_STAGE_BYTES = HALO ? 0 : 2 * TC_A_BYTES; // HALO: A lives in the patch buffers, stages hold B only
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + 2 * B_BYTES;
+  static constexpr int PATCH_BYTES = HALO ? 2 * TC_HALO_PLANE_BYTES : 0;      // one patch buffer: hi + lo plane
   static constexpr int OUT_STAGE_BYTES = NSPLIT * 2 * 128 * 64;   // per column part: hi + lo slabs of 128 rows x 32 ch
   // RES: the whole residual tile (BN/32 slabs x {hi, lo} x 128 rows x 64 B) is TMA-prefetched at tile start
   static constexpr int RES_STAGE_BYTES = (RES && !INPLACE) ? (BN / 32) * 2 * 128 * 64 : 0;
   static constexpr int SMEM_BYTES =
-      STAGES * STAGE_BYTES + OUT_STAGE_BYTES + RES_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+      2 * PATCH_BYTES + STAGES * STAGE_BYTES + OUT_STAGE_BYTES + RES_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
   static constexpr int TMEM_COLS = 4 * BN;          // D1[0], D1[1], D2[0], D2[1]  (256 or 512 columns)
   static constexpr int EPI_WARPS = 4 * NSPLIT;
   static constexpr int RES_WARP = 2 + EPI_WARPS;    // residual-tile TMA producer (RES kernels)
@@ -308,10 +327,10 @@ struct TcCfg {
 // free-running stage / chunk counters, so the producer prefetches the next tile's operands and the
 // tensor core starts the next tile while the epilogue warps are still storing the previous one
 // (D1 and D2 are double-buffered in TMEM).
-template <int BN, int STAGES, bool RES, int NSPLIT, bool INPLACE, bool PAIR>
-__global__ void __launch_bounds__(TcCfg<BN, STAGES, RES, NSPLIT, INPLACE, PAIR>::THREADS, 1)
+template <int BN, int STAGES, bool RES, int NSPLIT, bool INPLACE, bool PAIR, bool HALO>
+__global__ void __launch_bounds__(TcCfg<BN, STAGES, RES, NSPLIT, INPLACE, PAIR, HALO>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcArgs a) {
-  using Cfg = TcCfg<BN, STAGES, RES, NSPLIT, INPLACE, PAIR>;
+  using Cfg = TcCfg<BN, STAGES, RES, NSPLIT, INPLACE, PAIR, HALO>;
   constexpr int EPI_WARPS = Cfg::EPI_WARPS;
   // CTA pair: rank inside the 2-CTA cluster (0 = leader: arms the stage barriers, issues every MMA); scheduling unit =
   // the pair (sched_id of sched_n); logical tile t = (pair of M tiles, N tile), this CTA's M tile = 2 * pair + rank
@@ -322,7 +341,9 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
   // 1024 B alignment by OFFSET (not by integer round-trip) so the compiler keeps the shared address space
   // and emits LDS/STS for the staging buffers instead of generic LD/ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES;      // [2 halves][hi, lo][128 rows x 64 B], 64 B swizzle
+  uint8_t* patch = smem;                                      // HALO: [2 buffers][hi, lo][(th+2) x 10 pixels x 128 B]
+  uint8_t* stages = smem + 2 * Cfg::PATCH_BYTES;              // operand ring
+  uint8_t* out_stage = stages + STAGES * Cfg::STAGE_BYTES;    // [2 halves][hi, lo][128 rows x 64 B], 64 B swizzle
   uint8_t* res_stage = out_stage + Cfg::OUT_STAGE_BYTES;      // [BN/32 slabs][hi, lo][128 rows x 64 B] (RES only)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_stage + Cfg::RES_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -331,7 +352,9 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
   uint64_t* d2_empty_bar = acc_empty_bar + 2;        // [2]  D2[tbuf] drained
   uint64_t* res_full_bar = d2_empty_bar + 2;         // [4]  residual slab landed (TMA)
   uint64_t* res_empty_bar = res_full_bar + 4;        // [4]  residual slab consumed by its 4 epilogue warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty_bar + 4);
+  uint64_t* patch_full_bar = res_empty_bar + 4;      // [2]  HALO: patch buffer landed (TMA)
+  uint64_t* patch_empty_bar = patch_full_bar + 2;    // [2]  HALO: every MMA reading the patch buffer has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(patch_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
@@ -347,6 +370,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
     }
     // res_empty: the slab's four epilogue warps (separate residual staging) or the part's store leader (in place)
     for (int s = 0; s < 4; ++s) { mbar_init(&res_full_bar[s], 1); mbar_init(&res_empty_bar[s], INPLACE ? 1 : 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&patch_full_bar[s], 1); mbar_init(&patch_empty_bar[s], 1); }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -371,8 +395,9 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer: one (tap, 64-channel) slice per stage
-      const uint32_t stage_tx = 2u * (uint32_t)rows_valid * 128u + 2u * (uint32_t)Cfg::B_BYTES;
-      uint32_t git = 0;
+      const uint32_t stage_tx = (HALO ? 0u : 2u * (uint32_t)rows_valid * 128u) + 2u * (uint32_t)Cfg::B_BYTES;
+      const uint32_t patch_tx = 2u * (uint32_t)(a.th + 2) * (uint32_t)TC_HALO_PITCH;
+      uint32_t git = 0, gpatch = 0;
       TcSched sched(a.sk_mode, total_tiles, n_iters, sched_id, sched_n);
       TcItem item;
       while (sched.next(item)) {
@@ -380,15 +405,45 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
         const int nt = t % a.n_tiles, mt = PAIR ? 2 * (t / a.n_tiles) + pair_rank : t / a.n_tiles;
         const int x0 = (mt % a.tiles_w) * a.tw, y0 = ((mt / a.tiles_w) % a.tiles_h) * a.th;
         const int img0 = (mt / (a.tiles_w * a.tiles_h)) * a.nb, n0 = nt * BN;
+        int patch_cc = -1;
         for (int k = item.k0; k < item.k1; ++k, ++git) {
-          const int tap = k / cchunks, cc = k - tap * cchunks;
+          // K order: tap-major for the im2col kernels, 64-channel-slice-major for HALO (nine taps share one patch)
+          const int tap = HALO ? k % 9 : k / cchunks, cc = HALO ? k / 9 : k - tap * cchunks;
           const int r = tap / a.kw, s = tap % a.kw;
           const int iy = y0 * a.stride + r * a.rate - a.pad_t, ix = x0 * a.stride + s * a.rate - a.pad_l;
+          if (HALO && cc != patch_cc) {
+            patch_cc = cc;
+            const uint32_t pb = gpatch & 1u;
+            mbar_wait(&patch_empty_bar[pb], ((gpatch >> 1) & 1u) ^ 1u);
+            uint8_t* pbase = patch + pb * Cfg::PATCH_BYTES;
+            if (PAIR) {
+              if (pair_rank == 0) mbar_arrive_expect_tx(&patch_full_bar[pb], 2u * patch_tx);
+              tma_load_4d_2sm(pbase, &a.tm_a_hi, &patch_full_bar[pb], cc * 64, x0 - a.pad_l, y0 - a.pad_t, img0);
+              tma_load_4d_2sm(pbase + TC_HALO_PLANE_BYTES, &a.tm_a_lo, &patch_full_bar[pb], cc * 64, x0 - a.pad_l,
+                              y0 - a.pad_t, img0);
+            } else {
+              mbar_arrive_expect_tx(&patch_full_bar[pb], patch_tx);
+              tma_load_4d(pbase, &a.tm_a_hi, &patch_full_bar[pb], cc * 64, x0 - a.pad_l, y0 - a.pad_t, img0);
+              tma_load_4d(pbase + TC_HALO_PLANE_BYTES, &a.tm_a_lo, &patch_full_bar[pb], cc * 64, x0 - a.pad_l,
+                          y0 - a.pad_t, img0);
+            }
+            ++gpatch;
+          }
           const uint32_t st = git % STAGES, ph = (git / STAGES) & 1u;
           mbar_wait(&empty_bar[st], ph ^ 1u);
-          uint8_t* sbase = smem + st * Cfg::STAGE_BYTES;
+          uint8_t* sbase = stages + st * Cfg::STAGE_BYTES;
           const int kcol = tap * a.cin + cc * 64;
-          if (PAIR) {
+          if (HALO) {
+            if (PAIR) {
+              if (pair_rank == 0) mbar_arrive_expect_tx(&full_bar[st], 2u * stage_tx);
+              tma_load_2d_2sm(sbase, &a.tm_b_hi, &full_bar[st], kcol, n0 + pair_rank * (BN / 2));
+              tma_load_2d_2sm(sbase + Cfg::B_BYTES, &a.tm_b_lo, &full_bar[st], kcol, n0 + pair_rank * (BN / 2));
+            } else {
+              mbar_arrive_expect_tx(&full_bar[st], stage_tx);
+              tma_load_2d(sbase, &a.tm_b_hi, &full_bar[st], kcol, n0);
+              tma_load_2d(sbase + Cfg::B_BYTES, &a.tm_b_lo, &full_bar[st], kcol, n0);
+            }
+          } else if (PAIR) {
             // the leader arms its barrier for the bytes of BOTH CTAs; either CTA's loads complete on that barrier
             // (a tile of the odd CTA past the last M tile lies outside the tensor: zero-filled, same byte count)
             if (pair_rank == 0) mbar_arrive_expect_tx(&full_bar[st], 2u * stage_tx);
@@ -411,7 +466,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
       // ---------------- MMA issuer: per K=16 slice  D1 += Ahi*Bhi ;  D2 += Ahi*Blo + Alo*Bhi
       // (pair: only the leader issues; M = 256 spans both CTAs' A rows and accumulators)
       constexpr uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, BN);
-      uint32_t git = 0, gchunk = 0, tile_iter = 0;
+      uint32_t git = 0, gchunk = 0, tile_iter = 0, gpatch = 0;
       TcSched sched(a.sk_mode, total_tiles, n_iters, sched_id, sched_n);
       TcItem item;
       for (; sched.next(item); ++tile_iter) {
@@ -422,6 +477,8 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
         uint32_t d1 = 0, buf = 0;
         const int n_rel = item.k1 - item.k0;
         int chunk_begin = 0, chunk_stop = 0;           // current chunk = stages [chunk_begin, chunk_stop) of this item
+        int patch_cc = -1;
+        uint32_t pb = 0;
         for (int it = item.k0; it < item.k1; ++it, ++git) {
           const int rel = it - item.k0;
           if (rel == chunk_stop) {
@@ -436,11 +493,28 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           const uint32_t st = git % STAGES, ph = (git / STAGES) & 1u;
           mbar_wait(&full_bar[st], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
-          const uint64_t d_ahi = make_sw128_kmajor_desc(sa);
-          const uint64_t d_alo = make_sw128_kmajor_desc(sa + TC_A_BYTES);
-          const uint64_t d_bhi = make_sw128_kmajor_desc(sa + 2 * TC_A_BYTES);
-          const uint64_t d_blo = make_sw128_kmajor_desc(sa + 2 * TC_A_BYTES + Cfg::B_BYTES);
+          const uint32_t sa = smem_u32(stages + st * Cfg::STAGE_BYTES);
+          uint64_t d_ahi, d_alo;
+          if (HALO) {
+            const int cc = it / 9, tap = it - cc * 9;
+            if (cc != patch_cc) {
+              patch_cc = cc;
+              pb = gpatch & 1u;
+              mbar_wait(&patch_full_bar[pb], (gpatch >> 1) & 1u);
+              tc_fence_after();
+              ++gpatch;
+            }
+            // view of the patch shifted by tap (r, s): row 8 g + j of the operand = patch pixel (g + r, j + s)
+            const uint32_t pa = smem_u32(patch + pb * Cfg::PATCH_BYTES) + (uint32_t)((tap / 3) * TC_HALO_PITCH + (tap % 3) * 128);
+            const uint32_t boff = a.halo_baseoff ? (pa >> 7) & 7u : 0u;
+            d_ahi = make_sw128_kmajor_desc_sbo(pa, TC_HALO_PITCH, boff);
+            d_alo = make_sw128_kmajor_desc_sbo(pa + TC_HALO_PLANE_BYTES, TC_HALO_PITCH, boff);
+          } else {
+            d_ahi = make_sw128_kmajor_desc(sa);
+            d_alo = make_sw128_kmajor_desc(sa + TC_A_BYTES);
+          }
+          const uint64_t d_bhi = make_sw128_kmajor_desc(sa + Cfg::A_STAGE_BYTES);
+          const uint64_t d_blo = make_sw128_kmajor_desc(sa + Cfg::A_STAGE_BYTES + Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ko = (uint64_t)(k * 2);      // 16 fp16 = 32 B = 2 x 16 B units
@@ -456,6 +530,9 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           }
           // frees the smem slot once these MMAs retire (pair: in both CTAs)
           if (PAIR) umma_commit_2sm(&empty_bar[st], 0x3); else umma_commit(&empty_bar[st]);
+          if (HALO && (it + 1 == item.k1 || (it + 1) % 9 == 0)) {     // last tap of this item on the current patch
+            if (PAIR) umma_commit_2sm(&patch_empty_bar[pb], 0x3); else umma_commit(&patch_empty_bar[pb]);
+          }
           if (rel + 1 == chunk_stop) {
             // D1[buf] (and, on the last chunk, D2[tbuf]) complete -- published to the epilogue warps of both CTAs
             if (PAIR) umma_commit_2sm(&acc_full_bar[buf], 0x3); else umma_commit(&acc_full_bar[buf]);
@@ -902,15 +979,15 @@ void conv_workspace_free(ConvWorkspace& w) {
   w.partials = nullptr; w.flags = nullptr; w.ctas = 0;
 }
 
-template <int BN, int STAGES, bool RES, int NSPLIT = 2, bool INPLACE = false, bool PAIR = false>
+template <int BN, int STAGES, bool RES, int NSPLIT = 2, bool INPLACE = false, bool PAIR = false, bool HALO = false>
 static void launch_tc_cfg(const TcArgs& a, ConvWorkspace* sk, int streamk, int sm_reserve, cudaStream_t st) {
-  using Cfg = TcCfg<BN, STAGES, RES, NSPLIT, INPLACE, PAIR>;
+  using Cfg = TcCfg<BN, STAGES, RES, NSPLIT, INPLACE, PAIR, HALO>;
   // cudaFuncSetAttribute is per device: one flag per (kernel instance, device)
   static bool attr_set[LUMI_MAX_DEVICES] = {false};
   int dev = 0;
   LUMI_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= LUMI_MAX_DEVICES || !__atomic_load_n(&attr_set[dev], __ATOMIC_ACQUIRE)) {
-    LUMI_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE, PAIR>,
+    LUMI_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE, PAIR, HALO>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (dev >= 0 && dev < LUMI_MAX_DEVICES) __atomic_store_n(&attr_set[dev], true, __ATOMIC_RELEASE);
   }
@@ -952,12 +1029,12 @@ static void launch_tc_cfg(const TcArgs& a, ConvWorkspace* sk, int streamk, int s
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    LUMI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE, PAIR>, args));
+    LUMI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE, PAIR, HALO>, args));
     count_launch();
     return;
   }
   const int grid = units;
-  conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE, PAIR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(args);
+  conv_tc_kernel<BN, STAGES, RES, NSPLIT, INPLACE, PAIR, HALO><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(args);
   count_launch();
   LUMI_CUDA_CHECK(cudaGetLastError());
 }
@@ -971,10 +1048,26 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   int nb, th, tw;
   pick_tile(io.in.n, io.ho, io.wo, nb, th, tw);
   const int bn = (L.cout_pad % 128 == 0) ? 128 : 64;
+  // halo-patch kernels (3x3, stride 1, rate 1, SAME): tiles of th x 8 pixels of one image, th <= 16 chosen so that the
+  // rows of the map split evenly.  They trade M-tile occupancy (th * 8 <= 128 rows, and the weights stream once per
+  // tile) for ~6x less activation traffic, so they are used while the tile count stays within io.halo_tiles_pct of the generic one.
+  bool halo = false;
+  if (io.halo && L.kh == 3 && L.kw == 3 && L.stride == 1 && L.rate == 1 && io.pad_t == 1 && io.pad_l == 1 &&
+      !io.res.hi && !io.out_f32 && !io.in_pix_pitch && !io.in_row_pitch && !io.in_img_pitch) {
+    const int h_tiles = cdiv(io.ho, 16), h_th = cdiv(io.ho, h_tiles);
+    const long std_tiles = (long)cdiv(io.in.n, nb) * cdiv(io.ho, th) * cdiv(io.wo, tw);
+    const long halo_tiles = (long)io.in.n * h_tiles * cdiv(io.wo, TC_HALO_TW);
+    if (halo_tiles * 100 <= std_tiles * io.halo_tiles_pct) { halo = true; nb = 1; th = h_th; tw = TC_HALO_TW; }
+  }
+  if (halo) {            // the activation maps describe the PATCH box {64 ch, 10, th + 2, 1}
+    a.tm_a_hi = cached_act_map(io.in.hi, io.in.n, io.in.h, io.in.w, io.in.c, 1, th + 2, tw + 2, 1, 0, 0, 0);
+    a.tm_a_lo = cached_act_map(io.in.lo, io.in.n, io.in.h, io.in.w, io.in.c, 1, th + 2, tw + 2, 1, 0, 0, 0);
+  } else {
   a.tm_a_hi = cached_act_map(io.in.hi, io.in.n, io.in.h, io.in.w, io.in.c, nb, th, tw, L.stride, io.in_pix_pitch,
                              io.in_row_pitch, io.in_img_pitch);
   a.tm_a_lo = cached_act_map(io.in.lo, io.in.n, io.in.h, io.in.w, io.in.c, nb, th, tw, L.stride, io.in_pix_pitch,
                              io.in_row_pitch, io.in_img_pitch);
+  }
   const int kdim = L.kh * L.kw * L.cin;
   a.tm_b_hi = cached_wgt_map(L.w_hi, L.cout_pad, kdim, bn);
   a.tm_b_lo = cached_wgt_map(L.w_lo, L.cout_pad, kdim, bn);
@@ -994,6 +1087,19 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   a.chunk_head = 2 * TC_CHUNK_STAGES;
   a.chunk_tail = (io.chunk_tail >= 1 && io.chunk_tail <= TC_CHUNK_STAGES) ? io.chunk_tail : TC_CHUNK_STAGES;
   a.overflow = io.overflow_flag;
+  a.halo_baseoff = io.halo_baseoff;
+  if (halo) {
+    if (bn == 128 && io.halo >= 2) {           // CTA pair: each CTA its own patch, half of the weight tile
+      a.tm_b_hi = cached_wgt_map(L.w_hi, L.cout_pad, kdim, 64);
+      a.tm_b_lo = cached_wgt_map(L.w_lo, L.cout_pad, kdim, 64);
+      launch_tc_cfg<128, 6, false, 2, false, true, true>(a, io.sk, io.streamk, io.sm_reserve, st);
+    } else if (bn == 128) {
+      launch_tc_cfg<128, 3, false, 2, false, false, true>(a, io.sk, io.streamk, io.sm_reserve, st);
+    } else {
+      launch_tc_cfg<64, 6, false, 2, false, false, true>(a, io.sk, io.streamk, io.sm_reserve, st);
+    }
+    return;
+  }
   const bool res_tma = io.res.hi != nullptr && bn == 128 && L.cout % 128 == 0 && !io.out_f32;
   // CTA pairs (cta_group::2) for the long-K layers without residual: 48 KB of operands per CTA and stage, four stages
   const long n_iters_all = (long)L.kh * L.kw * (L.cin >> 6);

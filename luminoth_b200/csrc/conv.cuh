@@ -50,6 +50,9 @@ struct ConvIO {
   int streamk = 1;              // stream-K policy of THIS launch: 0 off, 1 auto (wave-quantisation heuristic), 2 whenever possible
   int chunk_tail = 2;           // stages per D1 chunk after the first eight stages of a tile (1, 2 or 4; see tc_chunk_end)
   int cta2 = 0;                 // CTA-pair (cta_group::2) kernel on residual-free layers with at least this many K stages per tile (0 = never)
+  int halo = 0;                 // halo-patch kernels on 3x3 stride-1 layers: 0 never, 1 single CTA, 2 CTA pairs where C_out % 128 == 0
+  int halo_tiles_pct = 150;     // ... while their M-tile count stays within this percentage of the generic kernel's
+  int halo_baseoff = 0;         // (bring-up switch) write the patch views' swizzle phase into the matrix descriptors
   int epi16 = 0;                // 16-epilogue-warp kernels on layers with at most this many K stages per tile (0 = never)
   int sm_reserve = 0;           // SMs a persistent launch leaves free (the engine's two-stream pipeline sets 8)
   // Optional strided ("Toeplitz") view of the input for the tcgen05 path: element pitches between

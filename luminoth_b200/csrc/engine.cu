@@ -119,6 +119,9 @@ struct lumi_engine {
   int conv_chunk_tail = 2;      // env LUMI_CONV_CHUNK_TAIL: D1 chunk length (stages) past the first eight stages of a tile
   int conv_cta2 = 64;           // env LUMI_CONV_2CTA: minimum K stages per tile for the CTA-pair kernel (0 = off); measured:
                                 // wins from ~64 stages (RPN 3x3x1024: 488 -> 460 us, SSD / R101-tail 3x3x512), loses 1-3 % below
+  int conv_halo = 0;            // env LUMI_CONV_HALO: halo-patch kernels on the 3x3 stride-1 layers (0 off, 1 single CTA, 2 CTA pairs)
+  int conv_halo_pct = 150;      // env LUMI_CONV_HALO_PCT: ... while the M-tile count stays within this percentage of the generic kernel's
+  int conv_halo_baseoff = 0;    // env LUMI_HALO_BASEOFF (bring-up)
   int conv_epi16 = 1;           // env LUMI_CONV_EPI16: 16-epilogue-warp kernels for tiles of at most this many K stages
   uint8_t* d_images = nullptr; size_t images_cap = 0;
   float* d_boxes = nullptr; float* d_scores = nullptr; int* d_labels = nullptr; int* d_counts = nullptr;
@@ -654,6 +657,9 @@ Act run_conv(Ctx& cx, const std::string& key, Act in, int padding, const Act* re
   io.sm_reserve = cx.sm_reserve;
   io.epi16 = cx.e->conv_epi16;
   io.cta2 = cx.e->conv_cta2;
+  io.halo = cx.e->conv_halo;
+  io.halo_tiles_pct = cx.e->conv_halo_pct;
+  io.halo_baseoff = cx.e->conv_halo_baseoff;
   io.chunk_tail = cx.e->conv_chunk_tail;
   if (!cx.dry) {
     const bool tc = cx.e->conv_impl == 1 && conv_tc_supported(L, io);
@@ -1163,6 +1169,9 @@ int lumi_finalize(lumi_engine* e) {
   if (const char* v = std::getenv("LUMI_GRAPHS")) e->use_graphs = std::atoi(v) != 0;
   if (const char* v = std::getenv("LUMI_CONV_EPI16")) e->conv_epi16 = std::max(0, std::min(8, std::atoi(v)));
   if (const char* v = std::getenv("LUMI_CONV_2CTA")) e->conv_cta2 = std::max(0, std::atoi(v));
+  if (const char* v = std::getenv("LUMI_CONV_HALO")) e->conv_halo = std::max(0, std::min(2, std::atoi(v)));
+  if (const char* v = std::getenv("LUMI_CONV_HALO_PCT")) e->conv_halo_pct = std::max(0, std::atoi(v));
+  if (const char* v = std::getenv("LUMI_HALO_BASEOFF")) e->conv_halo_baseoff = std::atoi(v);
   if (const char* v = std::getenv("LUMI_CONV_CHUNK_TAIL")) e->conv_chunk_tail = std::max(1, std::min(4, std::atoi(v)));
   if (e->max_batch >= 2) {
     conv_workspace_create(e->sk_ws[1]);

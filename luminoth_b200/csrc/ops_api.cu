@@ -5,6 +5,7 @@
 #include "conv.cuh"
 #include "ops.cuh"
 
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <vector>
@@ -81,7 +82,7 @@ int lumi_op_conv2d(const float* x, int n, int h, int w, int cin, const float* wg
     launch_f32_to_act(residual, res->a, st);
     io.res = res->a; io.res_stride = 1;
   }
-  if (impl >= 1 && impl <= 7) {
+  if (impl >= 1 && impl <= 11) {
     // 1 whole tiles, 2 stream-K forced (fp32 outputs written by the epilogue);
     // 3 / 4 / 5: the engine's inter-layer form -- fp16x2 split planes through the staged TMA-store epilogue (and the
     // TMA-prefetched residual) -- with the 8-warp epilogue (3), the 16-warp short-K kernels allowed (4), and 4 + stream-K (5)
@@ -93,11 +94,14 @@ int lumi_op_conv2d(const float* x, int n, int h, int w, int cin, const float* wg
       io.out_f32 = nullptr;
       io.epi16 = (impl == 4 || impl == 5) ? 8 : 0;
       io.cta2 = (impl == 6 || impl == 7) ? 1 : 0;   // 6 / 7: CTA-pair kernel wherever it applies (7: + stream-K forced)
+      io.halo = (impl == 8 || impl == 9) ? 1 : ((impl == 10 || impl == 11) ? 2 : 0);   // 8-11: halo-patch kernels (9, 11: + stream-K)
+      io.halo_tiles_pct = 1000000;                  // test hook: whenever the shape allows
+      if (const char* e = std::getenv("LUMI_HALO_BASEOFF")) io.halo_baseoff = std::atoi(e);
     }
     LUMI_REQUIRE(conv_tc_supported(L, io), "conv2d: this layer shape is not handled by the tensor-core kernel");
     ConvWorkspace sk;
     struct SkGuard { ConvWorkspace& w; ~SkGuard() { conv_workspace_free(w); } } skg{sk};
-    if (impl == 2 || impl == 5 || impl == 7) {
+    if (impl == 2 || impl == 5 || impl == 7 || impl == 9 || impl == 11) {
       conv_workspace_create(sk);
       io.sk = &sk;
       io.streamk = 2;

@@ -73,10 +73,16 @@ CONV_CASES = [
     ('b1_shortcut_64_256', 2, 38, 64, 64, 256, 1, 1, 1, 'SAME', False, 0),
     ('b2_conv3_128_512_res', 3, 19, 32, 128, 512, 1, 1, 1, 'SAME', True, 1),
     ('b3_shortcut_512_1024', 1, 38, 64, 512, 1024, 1, 1, 1, 'SAME', False, 0),
+    # 3x3 stride-1 layers for the halo-patch kernels: 13-row tiles; C_out = 64 with three channel slices, a ragged last
+    # tile column and a ragged last tile row; an odd number of M tiles (the CTA-pair kernel's idle half) with two N tiles
+    ('halo_38x64_128', 2, 38, 64, 128, 128, 3, 1, 1, 'SAME', False, 1),
+    ('halo_23x61_192_64', 1, 23, 61, 192, 64, 3, 1, 1, 'SAME', False, 1),
+    ('halo_75x20_64_256', 3, 75, 20, 64, 256, 3, 1, 1, 'SAME', False, 0),
 ]
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc_streamk', 'tc_split', 'tc_split_epi16', 'tc_split_epi16_streamk', 'tc_split_cta2', 'tc_split_cta2_streamk'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc_streamk', 'tc_split', 'tc_split_epi16', 'tc_split_epi16_streamk', 'tc_split_cta2', 'tc_split_cta2_streamk',
+                                  'tc_split_halo', 'tc_split_halo_streamk', 'tc_split_halo_cta2', 'tc_split_halo_cta2_streamk'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv2d_matches_oracle(case, impl):
     name, n, h, w, cin, cout, k, stride, rate, padding, use_res, act = case
@@ -84,6 +90,8 @@ def test_conv2d_matches_oracle(case, impl):
         pytest.skip('layer shape runs on the SIMT kernel by design')
     if impl.startswith('tc_split') and cout % 32 != 0:
         pytest.skip('split-plane outputs exist for cout % 32 == 0 (head layers write fp32)')
+    if 'halo' in impl and not (k == 3 and stride == 1 and rate == 1 and padding == 'SAME' and not use_res):
+        pytest.skip('the halo-patch kernels exist for 3x3 / stride 1 / rate 1 / SAME layers without residual')
     import zlib
     rng = np.random.default_rng(zlib.crc32(name.encode()))
     x = (rng.standard_normal((n, h, w, cin)) * 2).astype(np.float32)
