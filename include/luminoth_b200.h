@@ -194,6 +194,13 @@ int lumi_decode_jpeg(const unsigned char* data, size_t nbytes, int device, unsig
                      int out_on_device, int* height, int* width);
 const char* lumi_jpeg_last_error(void);
 
+/* ---- measurement hook (no reference counterpart, not on the predict path): cost of one tcgen05.mma kind::f16
+ * 128 x n x 16 in SM clocks, averaged over all SMs, for `iters` stages of twelve MMAs.  mode: 0 every MMA accumulates
+ * into the same TMEM tile, 1 the conv kernel's D1 / D2 / D2 pattern, 2 round-robin over three tiles, 3 over four.
+ * shifted_a: A descriptors of the halo kernels (start 128 B past the swizzle boundary, 1280 B group stride).
+ * fill: a second thread streams bulk copies into shared memory meanwhile; *fill_bytes_per_clk = its achieved rate. */
+int lumi_op_mma_probe(int mode, int n, int iters, int shifted_a, int fill, double* clk_per_mma, double* fill_bytes_per_clk);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, 'libluminoth_b200.so')
 OBJ_DIR = os.path.join(HERE, 'build')
-SOURCES = ['conv.cu', 'elementwise.cu', 'roi.cu', 'postproc.cu', 'engine.cu', 'ops_api.cu', 'jpeg.cu']
+SOURCES = ['conv.cu', 'elementwise.cu', 'roi.cu', 'postproc.cu', 'engine.cu', 'ops_api.cu', 'jpeg.cu', 'probe.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', 
               '--expt-relaxed-constexpr', '-I', os.path.join(ROOT, 'include')]

@@ -334,7 +334,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
   constexpr int EPI_WARPS = Cfg::EPI_WARPS;
   // CTA pair: rank inside the 2-CTA cluster (0 = leader: arms the stage barriers, issues every MMA); scheduling unit =
   // the pair (sched_id of sched_n); logical tile t = (pair of M tiles, N tile), this CTA's M tile = 2 * pair + rank
-  const int pair_rank = PAIR ? (int)cluster_ctarank() : 0;
+  // (warp-uniform values are routed through a shuffle so that the compiler KNOWS they are uniform: the TMA / MMA issue
+  // instructions take their operands from uniform registers, and operands it cannot prove uniform cost a
+  // five-R2UR "waterfall" loop around every single UTCHMMA / UTMALDG -- see the producer and issuer roles below)
+  const int pair_rank = PAIR ? __shfl_sync(0xffffffffu, (int)cluster_ctarank(), 0) : 0;
   const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int sched_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
@@ -356,7 +359,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
   uint64_t* patch_empty_bar = patch_full_bar + 2;    // [2]  HALO: every MMA reading the patch buffer has retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(patch_empty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
   const int total_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * a.n_tiles;
   const int rows_valid = a.nb * a.th * a.tw;
@@ -387,14 +390,15 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int cchunks = a.cin >> 6;
   const int n_iters = a.kh * a.kw * cchunks;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer: one (tap, 64-channel) slice per stage
+    {
+      // ---------------- TMA producer: one (tap, 64-channel) slice per stage.  The whole warp walks the schedule and
+      // waits on the barriers (every value stays warp-uniform); lane 0 issues the copies.
       const uint32_t stage_tx = (HALO ? 0u : 2u * (uint32_t)rows_valid * 128u) + 2u * (uint32_t)Cfg::B_BYTES;
       const uint32_t patch_tx = 2u * (uint32_t)(a.th + 2) * (uint32_t)TC_HALO_PITCH;
       uint32_t git = 0, gpatch = 0;
@@ -416,7 +420,8 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
             const uint32_t pb = gpatch & 1u;
             mbar_wait(&patch_empty_bar[pb], ((gpatch >> 1) & 1u) ^ 1u);
             uint8_t* pbase = patch + pb * Cfg::PATCH_BYTES;
-            if (PAIR) {
+            if (lane != 0) {
+            } else if (PAIR) {
               if (pair_rank == 0) mbar_arrive_expect_tx(&patch_full_bar[pb], 2u * patch_tx);
               tma_load_4d_2sm(pbase, &a.tm_a_hi, &patch_full_bar[pb], cc * 64, x0 - a.pad_l, y0 - a.pad_t, img0);
               tma_load_4d_2sm(pbase + TC_HALO_PLANE_BYTES, &a.tm_a_lo, &patch_full_bar[pb], cc * 64, x0 - a.pad_l,
@@ -433,7 +438,8 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           mbar_wait(&empty_bar[st], ph ^ 1u);
           uint8_t* sbase = stages + st * Cfg::STAGE_BYTES;
           const int kcol = tap * a.cin + cc * 64;
-          if (HALO) {
+          if (lane != 0) {
+          } else if (HALO) {
             if (PAIR) {
               if (pair_rank == 0) mbar_arrive_expect_tx(&full_bar[st], 2u * stage_tx);
               tma_load_2d_2sm(sbase, &a.tm_b_hi, &full_bar[st], kcol, n0 + pair_rank * (BN / 2));
@@ -462,9 +468,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && pair_rank == 0) {
+    if (pair_rank == 0) {
       // ---------------- MMA issuer: per K=16 slice  D1 += Ahi*Bhi ;  D2 += Ahi*Blo + Alo*Bhi
-      // (pair: only the leader issues; M = 256 spans both CTAs' A rows and accumulators)
+      // (pair: only the leader issues; M = 256 spans both CTAs' A rows and accumulators).  Whole warp walks and
+      // waits, lane 0 issues: descriptors and TMEM addresses live in uniform registers.
       constexpr uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, BN);
       uint32_t git = 0, gchunk = 0, tile_iter = 0, gpatch = 0;
       TcSched sched(a.sk_mode, total_tiles, n_iters, sched_id, sched_n);
@@ -515,6 +522,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           }
           const uint64_t d_bhi = make_sw128_kmajor_desc(sa + Cfg::A_STAGE_BYTES);
           const uint64_t d_blo = make_sw128_kmajor_desc(sa + Cfg::A_STAGE_BYTES + Cfg::B_BYTES);
+          if (lane == 0) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ko = (uint64_t)(k * 2);      // 16 fp16 = 32 B = 2 x 16 B units
@@ -536,8 +544,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           if (rel + 1 == chunk_stop) {
             // D1[buf] (and, on the last chunk, D2[tbuf]) complete -- published to the epilogue warps of both CTAs
             if (PAIR) umma_commit_2sm(&acc_full_bar[buf], 0x3); else umma_commit(&acc_full_bar[buf]);
-            ++gchunk;
           }
+          }
+          __syncwarp();
+          if (rel + 1 == chunk_stop) ++gchunk;
         }
       }
     }

@@ -1,0 +1,158 @@
+// Measurement hook (not on the product path): issue-rate probe of tcgen05.mma kind::f16 in the shapes conv_tc_kernel
+// uses.  One CTA per SM; operands sit still in shared memory (zeros), one thread issues `iters` stages of twelve
+// 128 x N x 16 MMAs in a chosen accumulator pattern and the elapsed SM clocks are reported per CTA.  Answers, without
+// the rest of the conv pipeline around it: what does an MMA of this shape cost when (a) every MMA accumulates into the
+// same TMEM tile, (b) in the D1 / D2 / D2 pattern of the split-operand conv, (c) round-robin over 3 or 4 tiles, (d) with
+// N = 256, (e) with a shifted (not 1024 B aligned) A view as in the halo kernels, and (f) while bulk copies stream into
+// the same shared memory at the rate the TMA producer does.
+#include "../../include/luminoth_b200.h"
+#include "common.cuh"
+
+#include <string>
+#include <vector>
+
+namespace lumi {
+
+struct ProbeArgs {
+  int mode;          // accumulator pattern, see lumi_op_mma_probe
+  int n;             // MMA N (128 or 256)
+  int iters;         // stages of 12 MMAs
+  int shifted_a;     // 1: A descriptors start 128 B past the 1024 B boundary with a 1280 B group stride
+  int fill_bytes;    // > 0: a second thread keeps bulk-copying this many bytes per stage-equivalent into shared memory
+  const uint8_t* fill_src;
+  long long* clocks; // [gridDim.x]
+};
+
+constexpr int PROBE_STAGE_BYTES = 2 * 16384 + 2 * 32768;   // A hi, A lo (128 rows) + B hi, B lo (up to 256 rows)
+constexpr int PROBE_STAGES = 2;
+constexpr int PROBE_FILL_BYTES = 32768;
+constexpr int PROBE_SMEM = PROBE_STAGES * PROBE_STAGE_BYTES + PROBE_FILL_BYTES + 1024 + 64;
+
+__global__ void __launch_bounds__(96, 1) mma_probe_kernel(const ProbeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* fill = smem + PROBE_STAGES * PROBE_STAGE_BYTES;
+  uint64_t* done_bar = reinterpret_cast<uint64_t*>(fill + PROBE_FILL_BYTES);
+  uint64_t* fill_bar = done_bar + 1;                 // [4]
+  volatile uint32_t* stop_flag = reinterpret_cast<volatile uint32_t*>(fill_bar + 4);
+  uint32_t* tmem_slot = const_cast<uint32_t*>(stop_flag) + 1;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (PROBE_STAGES * PROBE_STAGE_BYTES + PROBE_FILL_BYTES) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(done_bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&fill_bar[i], 1);
+    *stop_flag = 0;
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 1) {
+    const uint32_t idesc = make_idesc_f16(128, a.n);
+    const uint32_t acc_cols = (uint32_t)a.n;
+    long long t0 = 0;
+    if (lane == 0) t0 = clock64();
+    for (int it = 0; it < a.iters; ++it) {
+      const uint32_t sa = smem_u32(smem + (it % PROBE_STAGES) * PROBE_STAGE_BYTES);
+      uint64_t d_ahi, d_alo;
+      if (a.shifted_a) {
+        d_ahi = make_sw128_kmajor_desc_sbo(sa + 128, 1280, 0);
+        d_alo = make_sw128_kmajor_desc_sbo(sa + 128 + 2048, 1280, 0);   // (overlaps the hi plane: contents are irrelevant)
+      } else {
+        d_ahi = make_sw128_kmajor_desc(sa);
+        d_alo = make_sw128_kmajor_desc(sa + 16384);
+      }
+      const uint64_t d_bhi = make_sw128_kmajor_desc(sa + 32768);
+      const uint64_t d_blo = make_sw128_kmajor_desc(sa + 32768 + 32768);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ko = (uint64_t)(k * 2);
+          const int m = k * 3;          // running MMA index inside the stage
+          uint32_t t[3];
+          if (a.mode == 0) { t[0] = t[1] = t[2] = 0; }
+          else if (a.mode == 1) { t[0] = 0; t[1] = t[2] = 1; }
+          else if (a.mode == 2) { t[0] = 0; t[1] = 1; t[2] = 2; }
+          else { t[0] = (uint32_t)(m & 3); t[1] = (uint32_t)((m + 1) & 3); t[2] = (uint32_t)((m + 2) & 3); }
+          // (always accumulating: the accumulators start with whatever TMEM held, which is irrelevant for the timing)
+          umma_f16(tmem_base + (t[0] * acc_cols) % 512u, d_ahi + ko, d_bhi + ko, idesc, 1u);
+          umma_f16(tmem_base + (t[1] * acc_cols) % 512u, d_ahi + ko, d_blo + ko, idesc, 1u);
+          umma_f16(tmem_base + (t[2] * acc_cols) % 512u, d_alo + ko, d_bhi + ko, idesc, 1u);
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      umma_commit(done_bar);
+      mbar_wait(done_bar, 0);
+      const long long t1 = clock64();
+      a.clocks[blockIdx.x] = t1 - t0;
+      *stop_flag = 1;
+    }
+    __syncwarp();
+  } else if (warp == 0 && a.fill_bytes > 0) {
+    // bulk copies global -> shared at full tilt until the MMA thread is done (the rate is reported by the host from the
+    // copy count); they land in their own 32 KB window, i.e. they compete for the shared-memory port only
+    if (lane == 0) {
+      // four 8 KB copies in flight (ring of four windows, one barrier each)
+      uint32_t n = 0;
+      while (!*stop_flag) {
+        const uint32_t slot = n & 3u;
+        if (n >= 4) mbar_wait(&fill_bar[slot], ((n >> 2) - 1u) & 1u);
+        mbar_arrive_expect_tx(&fill_bar[slot], (uint32_t)(PROBE_FILL_BYTES / 4));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(fill + slot * (PROBE_FILL_BYTES / 4))),
+                       "l"(a.fill_src + (size_t)((blockIdx.x * 7 + n) % 256) * (PROBE_FILL_BYTES / 4)),
+                       "r"((uint32_t)(PROBE_FILL_BYTES / 4)), "r"(smem_u32(&fill_bar[slot]))
+                     : "memory");
+        ++n;
+      }
+      for (uint32_t m = (n >= 4 ? n - 4 : 0); m < n; ++m) mbar_wait(&fill_bar[m & 3u], (m >> 2) & 1u);   // drain
+      a.clocks[gridDim.x + blockIdx.x] = (long long)n;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace lumi
+
+extern "C" int lumi_op_mma_probe(int mode, int n, int iters, int shifted_a, int fill, double* clk_per_mma,
+                                 double* fill_bytes_per_clk) {
+  using namespace lumi;
+  try {
+    LUMI_REQUIRE((n == 128 || n == 256) && iters > 0 && mode >= 0 && mode <= 3, "mma_probe: bad arguments");
+    LUMI_REQUIRE(n == 128 || mode <= 1, "mma_probe: N = 256 has two accumulator tiles");
+    int dev = 0, sms = 0;
+    LUMI_CUDA_CHECK(cudaGetDevice(&dev));
+    LUMI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    LUMI_CUDA_CHECK(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PROBE_SMEM));
+    long long* d_clk = nullptr;
+    uint8_t* d_src = nullptr;
+    LUMI_CUDA_CHECK(cudaMalloc(&d_clk, 2 * sms * sizeof(long long)));
+    LUMI_CUDA_CHECK(cudaMemset(d_clk, 0, 2 * sms * sizeof(long long)));
+    LUMI_CUDA_CHECK(cudaMalloc(&d_src, (size_t)64 * PROBE_FILL_BYTES));
+    LUMI_CUDA_CHECK(cudaMemset(d_src, 0, (size_t)64 * PROBE_FILL_BYTES));
+    ProbeArgs a{mode, n, iters, shifted_a, fill ? PROBE_FILL_BYTES : 0, d_src, d_clk};
+    mma_probe_kernel<<<sms, 96, PROBE_SMEM>>>(a);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<long long> h(2 * sms);
+    if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_clk, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_clk); cudaFree(d_src);
+    LUMI_CUDA_CHECK(e);
+    double clk = 0, copies = 0;
+    for (int i = 0; i < sms; ++i) { clk += (double)h[i]; copies += (double)h[sms + i]; }
+    if (clk_per_mma) *clk_per_mma = clk / sms / ((double)iters * 12.0);
+    if (fill_bytes_per_clk) *fill_bytes_per_clk = clk > 0 ? copies * (PROBE_FILL_BYTES / 4) / clk : 0.0;
+    return LUMI_OK;
+  } catch (const std::exception& ex) {
+    return LUMI_EINVAL;
+  }
+}
