@@ -254,6 +254,15 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
                : "memory");
 }
 
+// One lane of the (converged) warp, chosen by the hardware.  ptxas knows that a branch on elect.sync runs in exactly one
+// thread and issues the uniform-operand instructions inside (UTCHMMA, UTMALDG, UTCBAR) directly; a branch on
+// `lane == 0` gets an elect-and-loop wrapper around every one of them.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):

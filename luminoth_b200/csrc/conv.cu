@@ -335,8 +335,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
   // CTA pair: rank inside the 2-CTA cluster (0 = leader: arms the stage barriers, issues every MMA); scheduling unit =
   // the pair (sched_id of sched_n); logical tile t = (pair of M tiles, N tile), this CTA's M tile = 2 * pair + rank
   // (warp-uniform values are routed through a shuffle so that the compiler KNOWS they are uniform: the TMA / MMA issue
-  // instructions take their operands from uniform registers, and operands it cannot prove uniform cost a
-  // five-R2UR "waterfall" loop around every single UTCHMMA / UTMALDG -- see the producer and issuer roles below)
+  // instructions take their operands from uniform registers.  Inside `if (lane == 0)` every operand counts as
+  // thread-varying and each UTCHMMA / UTMALDG gets a loop of ELECT + five R2UR around it; with the whole warp walking
+  // the schedule and an elect.sync branch around the issue itself, the twelve MMAs of a stage are twelve consecutive
+  // UTCHMMA instructions.  Measured: conv_tc 3.62 -> 3.42 ms per step for the uniform operands alone.)
   const int pair_rank = PAIR ? __shfl_sync(0xffffffffu, (int)cluster_ctarank(), 0) : 0;
   const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int sched_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -420,7 +422,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
             const uint32_t pb = gpatch & 1u;
             mbar_wait(&patch_empty_bar[pb], ((gpatch >> 1) & 1u) ^ 1u);
             uint8_t* pbase = patch + pb * Cfg::PATCH_BYTES;
-            if (lane != 0) {
+            if (!elect_one()) {
             } else if (PAIR) {
               if (pair_rank == 0) mbar_arrive_expect_tx(&patch_full_bar[pb], 2u * patch_tx);
               tma_load_4d_2sm(pbase, &a.tm_a_hi, &patch_full_bar[pb], cc * 64, x0 - a.pad_l, y0 - a.pad_t, img0);
@@ -438,7 +440,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           mbar_wait(&empty_bar[st], ph ^ 1u);
           uint8_t* sbase = stages + st * Cfg::STAGE_BYTES;
           const int kcol = tap * a.cin + cc * 64;
-          if (lane != 0) {
+          if (!elect_one()) {
           } else if (HALO) {
             if (PAIR) {
               if (pair_rank == 0) mbar_arrive_expect_tx(&full_bar[st], 2u * stage_tx);
@@ -522,7 +524,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           }
           const uint64_t d_bhi = make_sw128_kmajor_desc(sa + Cfg::A_STAGE_BYTES);
           const uint64_t d_blo = make_sw128_kmajor_desc(sa + Cfg::A_STAGE_BYTES + Cfg::B_BYTES);
-          if (lane == 0) {
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ko = (uint64_t)(k * 2);      // 16 fp16 = 32 B = 2 x 16 B units
@@ -552,7 +554,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
       }
     }
   } else if (RES && warp == Cfg::RES_WARP) {
-    if (lane == 0) {
+    {
       // ---------------- residual producer: the shortcut tile of each output tile, one 32-channel slab (hi + lo
       // plane) per barrier pair, refilled as soon as its four epilogue warps have read the previous tile's slab.
       // It runs on its own warp so that it never holds back the operand loads of the next tile.
@@ -573,11 +575,14 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           // consumption order: every column part works on its first slab, then on its second, ...
           const int sl = (i % NSPLIT) * (BN / 32 / NSPLIT) + (i / NSPLIT);
           mbar_wait(&res_empty_bar[sl], (tile_iter & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&res_full_bar[sl], slab_tx);
-          tma_load_4d(res_base + (sl * 2 + 0) * 8192, &a.tm_r_hi, &res_full_bar[sl], n0 + sl * 32,
-                      x0 * a.res_stride, y0 * a.res_stride, img0);
-          tma_load_4d(res_base + (sl * 2 + 1) * 8192, &a.tm_r_lo, &res_full_bar[sl], n0 + sl * 32,
-                      x0 * a.res_stride, y0 * a.res_stride, img0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&res_full_bar[sl], slab_tx);
+            tma_load_4d(res_base + (sl * 2 + 0) * 8192, &a.tm_r_hi, &res_full_bar[sl], n0 + sl * 32,
+                        x0 * a.res_stride, y0 * a.res_stride, img0);
+            tma_load_4d(res_base + (sl * 2 + 1) * 8192, &a.tm_r_lo, &res_full_bar[sl], n0 + sl * 32,
+                        x0 * a.res_stride, y0 * a.res_stride, img0);
+          }
+          __syncwarp();
         }
         ++tile_iter;
       }

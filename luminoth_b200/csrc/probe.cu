@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(96, 1) mma_probe_kernel(const ProbeArgs a) {
       }
       const uint64_t d_bhi = make_sw128_kmajor_desc(sa + 32768);
       const uint64_t d_blo = make_sw128_kmajor_desc(sa + 32768 + 32768);
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t ko = (uint64_t)(k * 2);
