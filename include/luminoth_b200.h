@@ -198,8 +198,15 @@ const char* lumi_jpeg_last_error(void);
  * 128 x n x 16 in SM clocks, averaged over all SMs, for `iters` stages of twelve MMAs.  mode: 0 every MMA accumulates
  * into the same TMEM tile, 1 the conv kernel's D1 / D2 / D2 pattern, 2 round-robin over three tiles, 3 over four.
  * shifted_a: A descriptors of the halo kernels (start 128 B past the swizzle boundary, 1280 B group stride).
- * fill: a second thread streams bulk copies into shared memory meanwhile; *fill_bytes_per_clk = its achieved rate. */
-int lumi_op_mma_probe(int mode, int n, int iters, int shifted_a, int fill, double* clk_per_mma, double* fill_bytes_per_clk);
+ * fill: a second thread streams bulk copies into shared memory meanwhile; *fill_bytes_per_clk = its achieved rate.
+ * ldtm_warps (0-8): that many warps keep reading another TMEM tile with tcgen05.ld.32x32b.x32 meanwhile, pausing
+ * ldtm_gap clocks between reads; *ldtm_bytes_per_clk = their achieved rate per SM.
+ * sync: 0 none, 1 one tcgen05.commit per stage, 2 the conv kernel's operand ring of depth `ring` without the copies
+ * (commit -> empty barrier -> helper warp -> full barrier -> issuer).  mmas_per_stage: 12, or 4 (hi*hi only).
+ * flags: 1 no tcgen05.fence after the ring wait, 2 spin on mbarrier.test_wait, 4 two issuing warps (hi*hi / cross terms). */
+int lumi_op_mma_probe(int mode, int n, int iters, int shifted_a, int fill, int ldtm_warps, int ldtm_gap,
+                      int sync, int ring, int mmas_per_stage, int flags, double* clk_per_mma,
+                      double* fill_bytes_per_clk, double* ldtm_bytes_per_clk);
 
 #ifdef __cplusplus
 }

@@ -213,6 +213,9 @@ struct TcArgs {
   int stride;                      // TMA traversal stride of the activation map (1 or 2)
   int chunk_head, chunk_tail;      // D1 chunk schedule, see tc_chunk_end()
   int halo_baseoff;                // HALO kernels: 1 = write the start address' swizzle phase into the descriptors
+  int dbg;                         // timing experiments (results are WRONG when set; env LUMI_CONV_DBG): 1 operand loads only for
+                                   // the first ring fill, 2 D1 drains without tcgen05.ld / adds, 4 no cross-term MMAs,
+                                   // 8 no output stores; 16 (results stay right) no tcgen05.fence after the operand-ring wait
   int* overflow;
   // stream-K (sk_mode != 0): the K loops of all tiles form one unit sequence that is cut into gridDim.x equal
   // contiguous ranges; a CTA that starts in the middle of a tile writes its partial accumulators to
@@ -440,7 +443,9 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           mbar_wait(&empty_bar[st], ph ^ 1u);
           uint8_t* sbase = stages + st * Cfg::STAGE_BYTES;
           const int kcol = tap * a.cin + cc * 64;
-          if (!elect_one()) {
+          if ((a.dbg & 1) && git >= (uint32_t)STAGES) {         // (experiment) stale operands: just flip the barrier
+            if (lane == 0 && pair_rank == 0) mbar_arrive(&full_bar[st]);
+          } else if (!elect_one()) {
           } else if (HALO) {
             if (PAIR) {
               if (pair_rank == 0) mbar_arrive_expect_tx(&full_bar[st], 2u * stage_tx);
@@ -501,7 +506,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           const bool first_of_chunk = rel == chunk_begin;
           const uint32_t st = git % STAGES, ph = (git / STAGES) & 1u;
           mbar_wait(&full_bar[st], ph);
-          tc_fence_after();
+          if (!(a.dbg & 16)) tc_fence_after();
           const uint32_t sa = smem_u32(stages + st * Cfg::STAGE_BYTES);
           uint64_t d_ahi, d_alo;
           if (HALO) {
@@ -530,10 +535,12 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
             const uint64_t ko = (uint64_t)(k * 2);      // 16 fp16 = 32 B = 2 x 16 B units
             if (PAIR) {
               umma_f16_2sm(d1, d_ahi + ko, d_bhi + ko, idesc, (!first_of_chunk || k > 0) ? 1u : 0u);
+              if (a.dbg & 4) continue;
               umma_f16_2sm(d2, d_ahi + ko, d_blo + ko, idesc, (it > item.k0 || k > 0) ? 1u : 0u);
               umma_f16_2sm(d2, d_alo + ko, d_bhi + ko, idesc, 1u);
             } else {
               umma_f16(d1, d_ahi + ko, d_bhi + ko, idesc, (!first_of_chunk || k > 0) ? 1u : 0u);
+              if (a.dbg & 4) continue;
               umma_f16(d2, d_ahi + ko, d_blo + ko, idesc, (it > item.k0 || k > 0) ? 1u : 0u);
               umma_f16(d2, d_alo + ko, d_bhi + ko, idesc, 1u);
             }
@@ -630,7 +637,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
         tc_fence_after();
 #pragma unroll
         for (int ch = 0; ch < HC / 32; ++ch) {
-          if (n0 + ch * 32 < a.cout) {                   // warp-uniform
+          if (n0 + ch * 32 < a.cout && !(a.dbg & 2)) {   // warp-uniform
             uint32_t r[32];
             tmem_ld_32x32b_x32(lane_base + (uint32_t)(buf * BN + half * HC + ch * 32), r);
             tmem_ld_wait();
@@ -795,7 +802,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
             fence_proxy_async();
             named_bar_sync(1 + half, 128);
             if (store_leader) {
-              if (!PAIR || mt < m_tiles) {       // (the odd CTA's tile past the last M tile has nothing to store)
+              if ((!PAIR || mt < m_tiles) && !(a.dbg & 8)) {       // (the odd CTA's tile past the last M tile has nothing to store)
                 tma_store_4d(&a.tm_o_hi, st_hi, c0, x0, y0, img0);
                 tma_store_4d(&a.tm_o_lo, st_lo, c0, x0, y0, img0);
               }
@@ -1103,6 +1110,18 @@ void launch_conv_tc(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
   a.chunk_tail = (io.chunk_tail >= 1 && io.chunk_tail <= TC_CHUNK_STAGES) ? io.chunk_tail : TC_CHUNK_STAGES;
   a.overflow = io.overflow_flag;
   a.halo_baseoff = io.halo_baseoff;
+  {
+    // bits 1-8 produce WRONG results (they remove work to time the rest): honoured only together with
+    // LUMI_ALLOW_WRONG_RESULTS=1, which bench.py / the tests never set
+    static const int dbg = [] {
+      const char* e = std::getenv("LUMI_CONV_DBG");
+      int v = e ? std::atoi(e) : 0;
+      const char* ok = std::getenv("LUMI_ALLOW_WRONG_RESULTS");
+      if ((v & 15) && !(ok && std::atoi(ok) == 1)) v &= ~15;
+      return v;
+    }();
+    a.dbg = dbg;
+  }
   if (halo) {
     if (bn == 128 && io.halo >= 2) {           // CTA pair: each CTA its own patch, half of the weight tile
       a.tm_b_hi = cached_wgt_map(L.w_hi, L.cout_pad, kdim, 64);

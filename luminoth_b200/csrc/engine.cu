@@ -117,8 +117,9 @@ struct lumi_engine {
   ConvWorkspace sk_ws[2];       // stream-K scratch, one per stream
   int conv_streamk = 1;         // 0 off, 1 auto, 2 whenever possible
   int conv_chunk_tail = 2;      // env LUMI_CONV_CHUNK_TAIL: D1 chunk length (stages) past the first eight stages of a tile
-  int conv_cta2 = 64;           // env LUMI_CONV_2CTA: minimum K stages per tile for the CTA-pair kernel (0 = off); measured:
-                                // wins from ~64 stages (RPN 3x3x1024: 488 -> 460 us, SSD / R101-tail 3x3x512), loses 1-3 % below
+  int conv_cta2 = 9;            // env LUMI_CONV_2CTA: minimum K stages per tile for the CTA-pair kernel (0 = off).  Measured per
+                                // layer (profiles/r2_conv_variants.txt): with the elect.sync issue path pairs win from 9 stages
+                                // (3x3x128: 66 -> 60 us, 3x3x256: 64 -> 57, RPN 3x3x1024: 461 -> 377); one leader issues for two SMs
   int conv_halo = 0;            // env LUMI_CONV_HALO: halo-patch kernels on the 3x3 stride-1 layers (0 off, 1 single CTA, 2 CTA pairs)
   int conv_halo_pct = 150;      // env LUMI_CONV_HALO_PCT: ... while the M-tile count stays within this percentage of the generic kernel's
   int conv_halo_baseoff = 0;    // env LUMI_HALO_BASEOFF (bring-up)
@@ -807,14 +808,17 @@ void forward_frcnn(Ctx& cx, const void* images, int n, int h, int w) {
   const bool fuse_mean = e->use_mean && !has_tail;                        // ROI crop+max-pool+mean in one kernel
   const bool need_pooled = !fuse_mean || e->debug_taps;
   Act pooled, feat;
+  float* fmap_f32 = cx.f32(fmap.numel());                                  // gather source of the ROI kernel
   if (need_pooled) pooled = cx.act(n * post, e->pooled_w, e->pooled_h, fmap.c);
   if (fuse_mean) feat = cx.act(n * post, 1, 1, fmap.c);
-  float* fmap_f32 = cx.f32(fmap.numel());                                  // gather source of the ROI kernel
   if (!cx.dry) {
     // algorithmic bytes: feature map once + rois + output (fp16x2 planes = 4 B / element)
     const double bytes = 4.0 * fmap.numel() + 16.0 * n * post + 4.0 * (double)(need_pooled ? pooled.numel() : 0) +
                          4.0 * (double)(fuse_mean ? feat.numel() : 0);
     ProfScope ps(cx.e, cx.dry, PC_ROI, bytes);
+    // (writing this fp32 copy from the last block3 conv's epilogue was tried in round 2: direct global stores from the
+    //  epilogue warps of the residual-slab kernel made that kernel's results flaky at production size -- plain delays in
+    //  the same place did not -- profiles/r2_conv_variants.txt; the separate 60 us pass stays)
     launch_act_to_f32(fmap, fmap_f32, cx.st);
     launch_roi_pool(fmap_f32, fmap.n, fmap.h, fmap.w, fmap.c, proposals, prop_counts, post, (float)h, (float)w,
                     e->pooled_h, e->pooled_w, pooled, fuse_mean ? feat : Act(), cx.st);

@@ -19,6 +19,14 @@ struct ProbeArgs {
   int iters;         // stages of 12 MMAs
   int shifted_a;     // 1: A descriptors start 128 B past the 1024 B boundary with a 1280 B group stride
   int fill_bytes;    // > 0: a second thread keeps bulk-copying this many bytes per stage-equivalent into shared memory
+  int ldtm_warps;    // > 0: this many further warps keep reading a TMEM tile with tcgen05.ld (32x32b.x32) meanwhile
+  int ldtm_gap;      // ... with this many clocks of pause between two reads of a warp
+  int sync;          // per-stage synchronisation around the MMAs: 1 tcgen05.commit to a barrier nobody waits on; 2 the conv
+                     // kernel's ring: commit -> empty[s], a helper warp answers full[s], the issuer waits full[s] (depth `ring`)
+  int ring;          // ring depth for sync = 2 (2..8)
+  int mmas;          // MMAs per stage: 12 (all), 4 (hi*hi only)
+  int flags;         // 1: no tcgen05.fence after the ring wait; 2: spin on mbarrier.test_wait instead of try_wait;
+                     // 4: TWO issuing warps -- warp 1 the four hi*hi MMAs of a stage, warp 2 the eight cross-term MMAs
   const uint8_t* fill_src;
   long long* clocks; // [gridDim.x]
 };
@@ -26,9 +34,9 @@ struct ProbeArgs {
 constexpr int PROBE_STAGE_BYTES = 2 * 16384 + 2 * 32768;   // A hi, A lo (128 rows) + B hi, B lo (up to 256 rows)
 constexpr int PROBE_STAGES = 2;
 constexpr int PROBE_FILL_BYTES = 32768;
-constexpr int PROBE_SMEM = PROBE_STAGES * PROBE_STAGE_BYTES + PROBE_FILL_BYTES + 1024 + 64;
+constexpr int PROBE_SMEM = PROBE_STAGES * PROBE_STAGE_BYTES + PROBE_FILL_BYTES + 1024 + 64 + 128;
 
-__global__ void __launch_bounds__(96, 1) mma_probe_kernel(const ProbeArgs a) {
+__global__ void __launch_bounds__(96 + 8 * 32, 1) mma_probe_kernel(const ProbeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* fill = smem + PROBE_STAGES * PROBE_STAGE_BYTES;
@@ -36,12 +44,15 @@ __global__ void __launch_bounds__(96, 1) mma_probe_kernel(const ProbeArgs a) {
   uint64_t* fill_bar = done_bar + 1;                 // [4]
   volatile uint32_t* stop_flag = reinterpret_cast<volatile uint32_t*>(fill_bar + 4);
   uint32_t* tmem_slot = const_cast<uint32_t*>(stop_flag) + 1;
+  uint64_t* ring_full = reinterpret_cast<uint64_t*>(smem + PROBE_STAGES * PROBE_STAGE_BYTES + PROBE_FILL_BYTES + 64);   // [8]
+  uint64_t* ring_empty = ring_full + 8;                                                                              // [8]
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < (PROBE_STAGES * PROBE_STAGE_BYTES + PROBE_FILL_BYTES) / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
-    mbar_init(done_bar, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&fill_bar[i], 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], (a.flags & 4) ? 2 : 1); }
+    mbar_init(done_bar, (a.flags & 4) ? 2 : 1);
     *stop_flag = 0;
     fence_mbar_init();
   }
@@ -53,7 +64,8 @@ __global__ void __launch_bounds__(96, 1) mma_probe_kernel(const ProbeArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  if (warp == 1) {
+  if (warp == 1 || (warp == 2 && (a.flags & 4))) {
+    const int part = (a.flags & 4) ? warp : 0;        // 0 everything, 1 the hi*hi MMAs, 2 the cross terms
     const uint32_t idesc = make_idesc_f16(128, a.n);
     const uint32_t acc_cols = (uint32_t)a.n;
     long long t0 = 0;
@@ -70,6 +82,19 @@ __global__ void __launch_bounds__(96, 1) mma_probe_kernel(const ProbeArgs a) {
       }
       const uint64_t d_bhi = make_sw128_kmajor_desc(sa + 32768);
       const uint64_t d_blo = make_sw128_kmajor_desc(sa + 32768 + 32768);
+      const uint32_t rs = (uint32_t)it % (uint32_t)a.ring, rph = ((uint32_t)it / (uint32_t)a.ring) & 1u;
+      if (a.sync == 2) {
+        if (a.flags & 2) {
+          uint32_t ok = 0;
+          do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(smem_u32(&ring_full[rs])), "r"(rph) : "memory");
+          } while (!ok);
+        } else {
+          mbar_wait(&ring_full[rs], rph);
+        }
+        if (!(a.flags & 1)) tc_fence_after();
+      }
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -81,10 +106,13 @@ __global__ void __launch_bounds__(96, 1) mma_probe_kernel(const ProbeArgs a) {
           else if (a.mode == 2) { t[0] = 0; t[1] = 1; t[2] = 2; }
           else { t[0] = (uint32_t)(m & 3); t[1] = (uint32_t)((m + 1) & 3); t[2] = (uint32_t)((m + 2) & 3); }
           // (always accumulating: the accumulators start with whatever TMEM held, which is irrelevant for the timing)
-          umma_f16(tmem_base + (t[0] * acc_cols) % 512u, d_ahi + ko, d_bhi + ko, idesc, 1u);
+          if (part != 2) umma_f16(tmem_base + (t[0] * acc_cols) % 512u, d_ahi + ko, d_bhi + ko, idesc, 1u);
+          if (a.mmas == 4 || part == 1) continue;
           umma_f16(tmem_base + (t[1] * acc_cols) % 512u, d_ahi + ko, d_blo + ko, idesc, 1u);
           umma_f16(tmem_base + (t[2] * acc_cols) % 512u, d_alo + ko, d_bhi + ko, idesc, 1u);
         }
+        if (a.sync == 1) umma_commit(&ring_empty[0]);
+        if (a.sync == 2) umma_commit(&ring_empty[rs]);
       }
       __syncwarp();
     }
@@ -92,10 +120,17 @@ __global__ void __launch_bounds__(96, 1) mma_probe_kernel(const ProbeArgs a) {
       umma_commit(done_bar);
       mbar_wait(done_bar, 0);
       const long long t1 = clock64();
-      a.clocks[blockIdx.x] = t1 - t0;
-      *stop_flag = 1;
+      if (warp == 1) { a.clocks[blockIdx.x] = t1 - t0; *stop_flag = 1; }
     }
     __syncwarp();
+  } else if (warp == 0 && a.sync == 2) {
+    // the conv kernel's producer without the copies: stage s is handed back as soon as its MMAs have retired
+    for (int it = 0; it < a.iters; ++it) {
+      const uint32_t rs = (uint32_t)it % (uint32_t)a.ring, rph = ((uint32_t)it / (uint32_t)a.ring) & 1u;
+      mbar_wait(&ring_empty[rs], rph ^ 1u);
+      if (lane == 0) mbar_arrive(&ring_full[rs]);
+      __syncwarp();
+    }
   } else if (warp == 0 && a.fill_bytes > 0) {
     // bulk copies global -> shared at full tilt until the MMA thread is done (the rate is reported by the host from the
     // copy count); they land in their own 32 KB window, i.e. they compete for the shared-memory port only
@@ -117,6 +152,24 @@ __global__ void __launch_bounds__(96, 1) mma_probe_kernel(const ProbeArgs a) {
       a.clocks[gridDim.x + blockIdx.x] = (long long)n;
     }
   }
+  else if (warp >= 3 && warp - 3 < a.ldtm_warps) {
+    // epilogue-style readers: warp w reads lanes 32 (w % 4) .. +31, 32 columns of the LAST accumulator tile (columns
+    // 384..511: never written in modes 0-2 with N = 128), as conv_tc_kernel's D1 drain does
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 384u + (uint32_t)(((warp - 3) >> 2) * 32);
+    uint32_t n = 0;
+    float sink = 0.f;
+    while (!*stop_flag) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sink += __uint_as_float(r[j]);
+      ++n;
+      if (a.ldtm_gap > 0) { const long long t = clock64(); while (clock64() - t < a.ldtm_gap) {} }
+    }
+    if (lane == 0) a.clocks[2 * gridDim.x + blockIdx.x * 8 + (warp - 3)] = (long long)n;
+    if (sink == 123.456f) a.clocks[0] = 0;      // keep the loads alive
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
@@ -124,32 +177,40 @@ __global__ void __launch_bounds__(96, 1) mma_probe_kernel(const ProbeArgs a) {
 
 }  // namespace lumi
 
-extern "C" int lumi_op_mma_probe(int mode, int n, int iters, int shifted_a, int fill, double* clk_per_mma,
-                                 double* fill_bytes_per_clk) {
+extern "C" int lumi_op_mma_probe(int mode, int n, int iters, int shifted_a, int fill, int ldtm_warps, int ldtm_gap,
+                                 int sync, int ring, int mmas_per_stage, int flags, double* clk_per_mma,
+                                 double* fill_bytes_per_clk, double* ldtm_bytes_per_clk) {
   using namespace lumi;
   try {
     LUMI_REQUIRE((n == 128 || n == 256) && iters > 0 && mode >= 0 && mode <= 3, "mma_probe: bad arguments");
     LUMI_REQUIRE(n == 128 || mode <= 1, "mma_probe: N = 256 has two accumulator tiles");
+    LUMI_REQUIRE(ldtm_warps >= 0 && ldtm_warps <= 8 && ldtm_gap >= 0, "mma_probe: at most 8 reader warps");
+    LUMI_REQUIRE(sync >= 0 && sync <= 2 && ring >= 2 && ring <= 8 && (mmas_per_stage == 12 || mmas_per_stage == 4) &&
+                 !(sync == 2 && fill) && !((flags & 4) && (mmas_per_stage != 12 || mode != 1)),
+                 "mma_probe: bad synchronisation arguments");
     int dev = 0, sms = 0;
     LUMI_CUDA_CHECK(cudaGetDevice(&dev));
     LUMI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     LUMI_CUDA_CHECK(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PROBE_SMEM));
     long long* d_clk = nullptr;
     uint8_t* d_src = nullptr;
-    LUMI_CUDA_CHECK(cudaMalloc(&d_clk, 2 * sms * sizeof(long long)));
-    LUMI_CUDA_CHECK(cudaMemset(d_clk, 0, 2 * sms * sizeof(long long)));
+    LUMI_CUDA_CHECK(cudaMalloc(&d_clk, 10 * sms * sizeof(long long)));
+    LUMI_CUDA_CHECK(cudaMemset(d_clk, 0, 10 * sms * sizeof(long long)));
     LUMI_CUDA_CHECK(cudaMalloc(&d_src, (size_t)64 * PROBE_FILL_BYTES));
     LUMI_CUDA_CHECK(cudaMemset(d_src, 0, (size_t)64 * PROBE_FILL_BYTES));
-    ProbeArgs a{mode, n, iters, shifted_a, fill ? PROBE_FILL_BYTES : 0, d_src, d_clk};
-    mma_probe_kernel<<<sms, 96, PROBE_SMEM>>>(a);
+    ProbeArgs a{mode, n, iters, shifted_a, fill ? PROBE_FILL_BYTES : 0, ldtm_warps, ldtm_gap, sync, ring, mmas_per_stage, flags, d_src, d_clk};
+    mma_probe_kernel<<<sms, 96 + 8 * 32, PROBE_SMEM>>>(a);
     cudaError_t e = cudaDeviceSynchronize();
-    std::vector<long long> h(2 * sms);
+    std::vector<long long> h(10 * sms);
     if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_clk, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(d_clk); cudaFree(d_src);
     LUMI_CUDA_CHECK(e);
     double clk = 0, copies = 0;
     for (int i = 0; i < sms; ++i) { clk += (double)h[i]; copies += (double)h[sms + i]; }
-    if (clk_per_mma) *clk_per_mma = clk / sms / ((double)iters * 12.0);
+    if (clk_per_mma) *clk_per_mma = clk / sms / ((double)iters * mmas_per_stage);
+    double reads = 0;
+    for (int i = 2 * sms; i < 10 * sms; ++i) reads += (double)h[i];
+    if (ldtm_bytes_per_clk) *ldtm_bytes_per_clk = clk > 0 ? reads * 4096.0 / clk : 0.0;     // per SM
     if (fill_bytes_per_clk) *fill_bytes_per_clk = clk > 0 ? copies * (PROBE_FILL_BYTES / 4) / clk : 0.0;
     return LUMI_OK;
   } catch (const std::exception& ex) {

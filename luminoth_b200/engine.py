@@ -62,7 +62,7 @@ SIGNATURES = {
                                         ctypes.c_int, _c_int_p, _c_int_p]),
     'lumi_jpeg_last_error': (ctypes.c_char_p, []),
     'lumi_op_last_error': (ctypes.c_char_p, []),
-    'lumi_op_mma_probe': (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_double)] * 2),
+    'lumi_op_mma_probe': (ctypes.c_int, [ctypes.c_int] * 11 + [ctypes.POINTER(ctypes.c_double)] * 3),
     'lumi_op_conv2d': (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] + [ctypes.c_int] * 6 +
                        [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2 + [ctypes.c_void_p, _c_int_p, _c_int_p,
                                                                       ctypes.c_void_p]),

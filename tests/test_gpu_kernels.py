@@ -73,6 +73,8 @@ CONV_CASES = [
     ('b1_shortcut_64_256', 2, 38, 64, 64, 256, 1, 1, 1, 'SAME', False, 0),
     ('b2_conv3_128_512_res', 3, 19, 32, 128, 512, 1, 1, 1, 'SAME', True, 1),
     ('b3_shortcut_512_1024', 1, 38, 64, 512, 1024, 1, 1, 1, 'SAME', False, 0),
+    # the block3 endpoint at its production size (several waves of tiles per CTA)
+    ('b3_conv3_endpoint', 8, 38, 64, 256, 1024, 1, 1, 1, 'SAME', True, 1),
     # 3x3 stride-1 layers for the halo-patch kernels: 13-row tiles; C_out = 64 with three channel slices, a ragged last
     # tile column and a ragged last tile row; an odd number of M tiles (the CTA-pair kernel's idle half) with two N tiles
     ('halo_38x64_128', 2, 38, 64, 128, 128, 3, 1, 1, 'SAME', False, 1),
