@@ -41,8 +41,6 @@ timeout -s KILL 400 python bench.py --workload frcnn_r101 --steps 10 --warmup 3 
 for b in 1 2; do timeout -s KILL 300 python bench.py --steps 50 --warmup 5 --per-gpu-batch $b --no-cpu-baseline > ${O}_bench_r50_latency_b$b.json 2>/dev/null; done
 timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file ${O}_launches_r50.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > ${O}_ncu_bench.log 2>&1
 echo "ncu launches exit $?" >> ${O}_summary.txt
-# small source-correlated report of the ROI and NMS kernels for local inspection
-timeout -s KILL 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:roi_pool|nms_mask|nms_prefilter" -c 4 -f -o ${O}_prof_post_small python bench.py --ncu-range --ncu-unpiped --no-cpu-baseline > ${O}_ncu_small.log 2>&1
 tail -n 6 ${O}_pytest_gpu.log; tail -n 2 ${O}_smoke.log
 python - <<'PY'
 import json

@@ -3,11 +3,14 @@
 # multi-device engine tests (two engines / two devices in one process).
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > gpurun_out/s_smi.txt 2>&1
+: > gpurun_out/s_summary.txt
+if [ -z "$SCALE_SKIP_TESTS" ]; then
 timeout -s KILL 200 python -m pytest tests/test_gpu_engine_state.py -m gpu -q -p no:cacheprovider -k "two_engines or second_device" --timeout 150 --timeout-method=thread > gpurun_out/s_pytest_state.log 2>&1
-echo "pytest engine state exit $?" > gpurun_out/s_summary.txt
+echo "pytest engine state exit $?" >> gpurun_out/s_summary.txt
+fi
 timeout -s KILL 200 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/s_bench_n1.json 2> gpurun_out/s_bench_n1.err
 echo "bench n1 exit $?" >> gpurun_out/s_summary.txt
-for n in 2 4 8; do
+for n in ${SCALE_NS:-2 4 8}; do
   NCCL_DEBUG=INFO NCCL_DEBUG_FILE=gpurun_out/s_nccl_n${n}_%h_%p.log timeout -s KILL 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2950$n bench.py --gpus $n --steps 20 --warmup 3 > gpurun_out/s_bench_n$n.json 2> gpurun_out/s_bench_n$n.err
   rc=$?
   echo "bench n$n exit $rc" >> gpurun_out/s_summary.txt
