@@ -115,6 +115,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe of a phase (try_wait may suspend the warp for a while when the phase is not complete yet)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -258,6 +270,9 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
 // thread and issues the uniform-operand instructions inside (UTCHMMA, UTMALDG, UTCBAR) directly; a branch on
 // `lane == 0` gets an elect-and-loop wrapper around every one of them.
 __device__ __forceinline__ bool elect_one() {
+#ifdef LUMI_NO_ELECT
+  return (threadIdx.x & 31u) == 0u;
+#endif
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred != 0;

@@ -215,7 +215,8 @@ struct TcArgs {
   int halo_baseoff;                // HALO kernels: 1 = write the start address' swizzle phase into the descriptors
   int dbg;                         // timing experiments (results are WRONG when set; env LUMI_CONV_DBG): 1 operand loads only for
                                    // the first ring fill, 2 D1 drains without tcgen05.ld / adds, 4 no cross-term MMAs,
-                                   // 8 no output stores; 16 (results stay right) no tcgen05.fence after the operand-ring wait
+                                   // 8 no output stores; 16 (results stay right) no tcgen05.fence after the operand-ring wait;
+                                   // 32 (results stay right) operand barrier of the next stage probed before this stage's MMAs
   int* overflow;
   // stream-K (sk_mode != 0): the K loops of all tiles form one unit sequence that is cut into gridDim.x equal
   // contiguous ranges; a CTA that starts in the middle of a tile writes its partial accumulators to
@@ -481,6 +482,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
       // waits, lane 0 issues: descriptors and TMEM addresses live in uniform registers.
       constexpr uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, BN);
       uint32_t git = 0, gchunk = 0, tile_iter = 0, gpatch = 0;
+      bool have_acc = false;                           // the "drained" barrier of the next chunk's D1 buffer was already seen
       TcSched sched(a.sk_mode, total_tiles, n_iters, sched_id, sched_n);
       TcItem item;
       for (; sched.next(item); ++tile_iter) {
@@ -493,20 +495,28 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
         int chunk_begin = 0, chunk_stop = 0;           // current chunk = stages [chunk_begin, chunk_stop) of this item
         int patch_cc = -1;
         uint32_t pb = 0;
+        bool have_stage = false;                       // the operand barrier of this stage was already seen complete
         for (int it = item.k0; it < item.k1; ++it, ++git) {
           const int rel = it - item.k0;
           if (rel == chunk_stop) {
             chunk_begin = rel;
             chunk_stop = tc_chunk_end(rel, n_rel, a.chunk_head, a.chunk_tail);
             buf = gchunk & 1u;
-            mbar_wait(&acc_empty_bar[buf], ((gchunk >> 1) & 1u) ^ 1u);    // D1[buf] drained
+            if (!have_acc) mbar_wait(&acc_empty_bar[buf], ((gchunk >> 1) & 1u) ^ 1u);    // D1[buf] drained
             tc_fence_after();
             d1 = tmem_base + buf * BN;
+            // (dbg 32) the other D1 buffer, needed by the next chunk: usually drained long ago
+            have_acc = (a.dbg & 32) ? mbar_test_wait(&acc_empty_bar[buf ^ 1u], ((((gchunk + 1u) >> 1) & 1u) ^ 1u)) : false;
           }
           const bool first_of_chunk = rel == chunk_begin;
           const uint32_t st = git % STAGES, ph = (git / STAGES) & 1u;
-          mbar_wait(&full_bar[st], ph);
+          if (!have_stage) mbar_wait(&full_bar[st], ph);
           if (!(a.dbg & 16)) tc_fence_after();
+          // (experiment, dbg 32) look at the NEXT stage's barrier before this stage's MMAs are issued: the issuing thread
+          // blocks in the UTCHMMA queue anyway, and a satisfied wait between two stages costs ~100 exposed clocks
+          have_stage = false;
+          if ((a.dbg & 32) && it + 1 < item.k1)
+            have_stage = mbar_test_wait(&full_bar[(git + 1) % STAGES], ((git + 1) / STAGES) & 1u);
           const uint32_t sa = smem_u32(stages + st * Cfg::STAGE_BYTES);
           uint64_t d_ahi, d_alo;
           if (HALO) {
@@ -561,7 +571,11 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
       }
     }
   } else if (RES && warp == Cfg::RES_WARP) {
-    {
+    // ONE lane walks this role (unlike the producer / issuer warps).  The whole-warp form -- 32 lanes polling the slab
+    // barriers, one elected lane issuing -- made the results of the two-stream pipeline differ from run to run at
+    // production size (scripts/determinism_diag.py; elect.sync or `lane == 0` alike; single stream never), which the
+    // single-lane form does not.  Not understood; the eight copies per tile are not worth the risk.
+    if (lane == 0) {
       // ---------------- residual producer: the shortcut tile of each output tile, one 32-channel slab (hi + lo
       // plane) per barrier pair, refilled as soon as its four epilogue warps have read the previous tile's slab.
       // It runs on its own warp so that it never holds back the operand loads of the next tile.
@@ -582,14 +596,13 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
           // consumption order: every column part works on its first slab, then on its second, ...
           const int sl = (i % NSPLIT) * (BN / 32 / NSPLIT) + (i / NSPLIT);
           mbar_wait(&res_empty_bar[sl], (tile_iter & 1u) ^ 1u);
-          if (elect_one()) {
+          {
             mbar_arrive_expect_tx(&res_full_bar[sl], slab_tx);
             tma_load_4d(res_base + (sl * 2 + 0) * 8192, &a.tm_r_hi, &res_full_bar[sl], n0 + sl * 32,
                         x0 * a.res_stride, y0 * a.res_stride, img0);
             tma_load_4d(res_base + (sl * 2 + 1) * 8192, &a.tm_r_lo, &res_full_bar[sl], n0 + sl * 32,
                         x0 * a.res_stride, y0 * a.res_stride, img0);
           }
-          __syncwarp();
         }
         ++tile_iter;
       }
