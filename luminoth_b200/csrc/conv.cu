@@ -215,8 +215,7 @@ struct TcArgs {
   int halo_baseoff;                // HALO kernels: 1 = write the start address' swizzle phase into the descriptors
   int dbg;                         // timing experiments (results are WRONG when set; env LUMI_CONV_DBG): 1 operand loads only for
                                    // the first ring fill, 2 D1 drains without tcgen05.ld / adds, 4 no cross-term MMAs,
-                                   // 8 no output stores; 16 (results stay right) no tcgen05.fence after the operand-ring wait;
-                                   // 32 (results stay right) operand barrier of the next stage probed before this stage's MMAs
+                                   // 8 no output stores; 16 (results stay right) no tcgen05.fence after the operand-ring wait
   int* overflow;
   // stream-K (sk_mode != 0): the K loops of all tiles form one unit sequence that is cut into gridDim.x equal
   // contiguous ranges; a CTA that starts in the middle of a tile writes its partial accumulators to
@@ -482,7 +481,6 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
       // waits, lane 0 issues: descriptors and TMEM addresses live in uniform registers.
       constexpr uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, BN);
       uint32_t git = 0, gchunk = 0, tile_iter = 0, gpatch = 0;
-      bool have_acc = false;                           // the "drained" barrier of the next chunk's D1 buffer was already seen
       TcSched sched(a.sk_mode, total_tiles, n_iters, sched_id, sched_n);
       TcItem item;
       for (; sched.next(item); ++tile_iter) {
@@ -495,28 +493,22 @@ conv_tc_kernel(const __grid_constant__ TcArgs a) {
         int chunk_begin = 0, chunk_stop = 0;           // current chunk = stages [chunk_begin, chunk_stop) of this item
         int patch_cc = -1;
         uint32_t pb = 0;
-        bool have_stage = false;                       // the operand barrier of this stage was already seen complete
         for (int it = item.k0; it < item.k1; ++it, ++git) {
           const int rel = it - item.k0;
           if (rel == chunk_stop) {
             chunk_begin = rel;
             chunk_stop = tc_chunk_end(rel, n_rel, a.chunk_head, a.chunk_tail);
             buf = gchunk & 1u;
-            if (!have_acc) mbar_wait(&acc_empty_bar[buf], ((gchunk >> 1) & 1u) ^ 1u);    // D1[buf] drained
+            mbar_wait(&acc_empty_bar[buf], ((gchunk >> 1) & 1u) ^ 1u);    // D1[buf] drained
             tc_fence_after();
             d1 = tmem_base + buf * BN;
-            // (dbg 32) the other D1 buffer, needed by the next chunk: usually drained long ago
-            have_acc = (a.dbg & 32) ? mbar_test_wait(&acc_empty_bar[buf ^ 1u], ((((gchunk + 1u) >> 1) & 1u) ^ 1u)) : false;
           }
           const bool first_of_chunk = rel == chunk_begin;
           const uint32_t st = git % STAGES, ph = (git / STAGES) & 1u;
-          if (!have_stage) mbar_wait(&full_bar[st], ph);
+          // (probing the NEXT stage's barrier before this stage's MMAs are issued, so that the satisfied wait costs
+          //  nothing between two stages, was measured: no gain -- conv 3.265 vs 3.281 ms)
+          mbar_wait(&full_bar[st], ph);
           if (!(a.dbg & 16)) tc_fence_after();
-          // (experiment, dbg 32) look at the NEXT stage's barrier before this stage's MMAs are issued: the issuing thread
-          // blocks in the UTCHMMA queue anyway, and a satisfied wait between two stages costs ~100 exposed clocks
-          have_stage = false;
-          if ((a.dbg & 32) && it + 1 < item.k1)
-            have_stage = mbar_test_wait(&full_bar[(git + 1) % STAGES], ((git + 1) / STAGES) & 1u);
           const uint32_t sa = smem_u32(stages + st * Cfg::STAGE_BYTES);
           uint64_t d_ahi, d_alo;
           if (HALO) {
