@@ -43,7 +43,7 @@ ref = load('r2_bench_reference_arm.json')
 if ref:
     print('Reference arm (`bench.py --impl reference`): %s' % json.dumps({k: ref[k] for k in ref if k in ('value', 'unit', 'impl', 'ms_per_step')}))
 print()
-print('| GPUs (one box, weak scaling, per-GPU batch 8) | images/s | ms / step | efficiency vs N = 1 of the same box |')
+print('| GPUs (weak scaling, per-GPU batch 8; N = 1, 2, 4 on one 4-GPU box, N = 8 on an 8-GPU box) | images/s | ms / step | efficiency vs N × the N = 1 rate of the 4-GPU box |')
 print('|---|---|---|---|')
 base = None
 for n in (1, 2, 4, 8):
