@@ -3,16 +3,21 @@
 //  * conv_simt_kernel : fp32 implicit GEMM on CUDA cores. Handles every shape
 //    (C_in = 3 stem, stride 2, FC layers); also the on-GPU cross-check of the
 //    tensor-core kernel.
-//  * conv_tc_kernel   : tcgen05 implicit GEMM, stride 1, C_in % 64 == 0.
+//  * conv_tc_kernel   : tcgen05 implicit GEMM, stride 1 or 2, C_in % 64 == 0.
 //    Activations and weights are fp16 (hi, lo) split planes; each K=16 slice
-//    issues three kind::f16 MMAs  Ahi*Bhi + Ahi*Blo + Alo*Bhi  into one fp32
-//    TMEM accumulator (fp32-class accuracy, SURVEY section 7 "precision").
-//    im2col is fused: the producer issues one 4-D TMA box
+//    issues three kind::f16 MMAs  Ahi*Bhi + Ahi*Blo + Alo*Bhi  into fp32 TMEM
+//    accumulators (hi*hi into a double-buffered tile D1 that the epilogue warps
+//    drain in short chunks, the cross terms into D2 -- fp32-class accuracy,
+//    DESIGN section 3).  im2col is fused: the producer issues one 4-D TMA box
 //    {64 ch, tw, th, nb} per filter tap at shifted (possibly negative)
 //    coordinates; out-of-bounds elements are zero-filled by TMA, which IS the
-//    TF SAME zero padding.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer
-//    + TMEM owner, warps 2-5 epilogue (TMEM -> regs -> scale/bias (folded BN)
-//    -> +residual -> relu/relu6 -> hi/lo split -> NHWC store).
+//    TF SAME zero padding.  Persistent CTAs (whole tiles or stream-K), warp
+//    roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner (both walk the
+//    schedule as whole warps, one elected lane issues), 8 or 16 epilogue warps
+//    (TMEM -> regs -> scale/bias (folded BN) -> +residual -> relu/relu6 ->
+//    hi/lo split -> swizzled staging -> TMA store), one residual-slab producer
+//    lane in the RES kernels.  Variants: CTA pairs (tcgen05 cta_group::2) and
+//    the halo-patch kernels for 3x3 layers.
 //
 // Replaces slim conv2d+batch_norm+relu (luminoth/models/base/base_network.py:143-151),
 // snt.Conv2D (models/fasterrcnn/rpn.py:69-90, models/ssd/ssd.py:83-96,
