@@ -30,6 +30,22 @@ def test_library_exports_every_declared_symbol():
     assert lib.lumi_version().startswith(b'luminoth_b200')
 
 
+def test_library_is_blackwell_native_sass():
+    """The built library carries the sm_100a instructions the design claims and no legacy tensor path:
+    tcgen05.mma (UTCHMMA, and .2CTA for the CTA-pair kernels), TMA tensor loads / stores, tcgen05.ld / commit."""
+    import shutil
+    import subprocess
+    from luminoth_b200 import build as B
+    exe = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(exe) or not os.path.exists(B.LIB):
+        pytest.skip('cuobjdump or the built library is not available')
+    sass = subprocess.run([exe, '-sass', B.LIB], capture_output=True, text=True).stdout
+    assert 'sm_100a' in sass
+    for mnemonic in ('UTCHMMA ', 'UTCHMMA.2CTA', 'UTMALDG.4D', 'UTMASTG.4D', 'LDTM', 'UTCBAR', 'ELECT'):
+        assert mnemonic in sass, mnemonic
+    assert not re.search(r'\bHMMA\b|\bHGMMA\b', sass), 'legacy tensor-core instructions in the library'
+
+
 def test_engine_has_no_cpu_fallback():
     lib, engine = _built_lib()
     if lib.lumi_device_count() > 0:
