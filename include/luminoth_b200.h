@@ -207,6 +207,9 @@ const char* lumi_jpeg_last_error(void);
 int lumi_op_mma_probe(int mode, int n, int iters, int shifted_a, int fill, int ldtm_warps, int ldtm_gap,
                       int sync, int ring, int mmas_per_stage, int flags, double* clk_per_mma,
                       double* fill_bytes_per_clk, double* ldtm_bytes_per_clk);
+/* Second measurement hook: do the 32 lanes of one `mbarrier.try_wait` warp instruction ever get different answers?  One CTA
+ * per SM, `rounds` barrier phases; *diverged_rounds = rounds (summed over CTAs) in which the lanes' attempt counts differed. */
+int lumi_op_trywait_probe(int rounds, unsigned* diverged_rounds, unsigned* max_spread, unsigned* mean_attempts);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,7 @@ SIGNATURES = {
     'lumi_jpeg_last_error': (ctypes.c_char_p, []),
     'lumi_op_last_error': (ctypes.c_char_p, []),
     'lumi_op_mma_probe': (ctypes.c_int, [ctypes.c_int] * 11 + [ctypes.POINTER(ctypes.c_double)] * 3),
+    'lumi_op_trywait_probe': (ctypes.c_int, [ctypes.c_int] + [ctypes.POINTER(ctypes.c_uint)] * 3),
     'lumi_op_conv2d': (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] + [ctypes.c_int] * 6 +
                        [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2 + [ctypes.c_void_p, _c_int_p, _c_int_p,
                                                                       ctypes.c_void_p]),
